@@ -1,0 +1,62 @@
+"""Shared fixtures.  `gpu` marks tests that need a real B200 (run by the driver with -m gpu)."""
+import glob
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200)")
+
+
+SOLVER_FIXTURES = sorted(
+    os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, "*.npz"))
+    if os.path.basename(f)[:-4] not in ("extract", "mapper"))
+
+
+def load_golden(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def golden_cfg(d):
+    """SE3MPCConfig overrides stored with a fixture (keys cfg_*)."""
+    cfg = {k[4:]: float(d[k]) for k in d.files if k.startswith("cfg_")}
+    if "max_iterations" in cfg:
+        cfg["max_iterations"] = int(cfg["max_iterations"])
+    return cfg
+
+
+# Tolerances of BASELINE.json north_star (fp64 parity mode)
+COST_RTOL = 1e-5
+CTRL_ATOL = 1e-4
+
+
+def assert_solution_parity(got, d, what=""):
+    """got: object with x (B,9N), cost, nit, nfev, status, attitudes, body_rates, thrusts, accelerations."""
+    fun = d["fun"]
+    relf = np.abs(np.asarray(got.cost) - fun) / np.maximum(np.abs(fun), 1.0)
+    dx = np.abs(np.asarray(got.x) - d["x"]).max(axis=1)
+    bad = np.where((relf > COST_RTOL) | (dx > CTRL_ATOL))[0]
+    assert bad.size == 0, f"{what}: {bad.size} problems out of tolerance, first {bad[:5]}, relf {relf[bad[:5]]}, dx {dx[bad[:5]]}"
+    for k in ("nit", "nfev", "status"):
+        mism = np.where(np.asarray(getattr(got, k)) != d[k])[0]
+        assert mism.size == 0, f"{what}: {k} differs on {mism.size} problems, first {mism[:5]}: got {np.asarray(getattr(got, k))[mism[:5]]} want {d[k][mism[:5]]}"
+    np.testing.assert_allclose(got.accelerations, d["accelerations"], atol=1e-4 / 1.0, rtol=0)
+    np.testing.assert_allclose(got.thrusts, d["thrusts"], atol=1e-4, rtol=0)
+    np.testing.assert_allclose(got.attitudes, d["attitudes"], atol=1e-6, rtol=0)
+    # body rates are finite differences of R over dt: scale the tolerance by 1/dt
+    np.testing.assert_allclose(got.body_rates, d["body_rates"], atol=1e-4 / float(d["dt"]) * 1e-2 + 1e-6, rtol=1e-6)
+
+
+@pytest.fixture(scope="session")
+def oracle_mod():
+    import oracle
+    oracle.build()
+    return oracle

@@ -1,0 +1,14 @@
+"""dart_planner_b200 -- B200-native batched SE(3)-MPC solve path for DART-Planner.
+
+Drop-in for `dart_planner.planning.se3_mpc_planner.SE3MPCPlanner` (same plan/config API)
+plus a batched entry point (`plan_batch`) that solves thousands of independent problems per
+call on hand-written sm_100a kernels through a C ABI (include/dart_se3mpc.h).
+There is no CPU fallback.
+"""
+from .config import SE3MPCConfig, load_planner_config  # noqa: F401
+from .types import DroneState, Trajectory  # noqa: F401
+from .planner import BatchSolution, SE3MPCPlanner, plan_batch, solve_batch_tensors  # noqa: F401
+from .mapper import DenseOccupancyGrid  # noqa: F401
+
+__all__ = ["SE3MPCConfig", "load_planner_config", "DroneState", "Trajectory", "SE3MPCPlanner",
+           "BatchSolution", "plan_batch", "solve_batch_tensors", "DenseOccupancyGrid"]

@@ -1,0 +1,76 @@
+"""In-tree build of the CUDA library (sm_100a only).  `python -m dart_planner_b200.build`."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+OBJDIR = os.path.join(LIBDIR, "obj")
+LIB = os.path.join(LIBDIR, "libdart_se3mpc.so")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-lineinfo", "-std=c++17", "--extended-lambda", "-Xcompiler", "-fPIC"]
+# per-file extra flags; the mapper needs unfused multiply/add for bit-exact voxel indices
+UNITS = {
+    "se3mpc_kernels.cu": [],
+    "mapper_kernels.cu": ["-fmad=false"],
+    "probe_kernels.cu": [],
+}
+HEADERS = [os.path.join(CSRC, "se3mpc_core.cuh"),
+           os.path.join(HERE, "..", "include", "dart_se3mpc.h")]
+
+
+def nvcc() -> str:
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found: the CUDA library cannot be built")
+    return exe
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def _compile(unit, flags, verbose):
+    src = os.path.join(CSRC, unit)
+    obj = os.path.join(OBJDIR, unit.replace(".cu", ".o"))
+    if not _stale(obj, [src] + HEADERS):
+        return obj, ""
+    cmd = [nvcc()] + ARCH + COMMON + flags + ["-Xptxas", "-v", "-c", src, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {unit}:\n{r.stderr}")
+    if verbose:
+        print(r.stderr)
+    return obj, r.stderr
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(OBJDIR, exist_ok=True)
+    if force:
+        for f in os.listdir(OBJDIR):
+            os.remove(os.path.join(OBJDIR, f))
+    with ThreadPoolExecutor(len(UNITS)) as ex:
+        res = list(ex.map(lambda kv: _compile(kv[0], kv[1], verbose), UNITS.items()))
+    objs = [o for o, _ in res]
+    log = "\n".join(l for _, l in res if l)
+    if log:
+        with open(os.path.join(LIBDIR, "ptxas.log"), "w") as fh:
+            fh.write(log)
+    if _stale(LIB, objs):
+        cmd = [nvcc()] + ARCH + ["-shared", "-o", LIB] + objs
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,374 @@
+/*
+ * se3mpc_kernels.cu -- sm_100a kernels + C ABI (include/dart_se3mpc.h) of the batched
+ * SE(3)-MPC solve.  One problem per sub-warp (see se3mpc_core.cuh); a persistent grid walks
+ * the batch with a grid-stride loop.  I/O is batch-major SoA so the 32/LANES problems of a
+ * warp touch consecutive addresses of every row.
+ *
+ * Replaces: SE3MPCPlanner._solve_se3_mpc (se3_mpc_planner.py:230-280) for B problems.
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+
+#include "se3mpc_core.cuh"
+
+using namespace dartb200;
+
+namespace {
+
+std::atomic<long long> g_launches{0};
+thread_local char g_err[256] = "";
+
+struct SolveArgs {
+    long long B, ld;
+    const double *p0, *v0, *goal;
+    const unsigned char *has_goal;
+    const double *x_warm;
+    const unsigned char *warm_mask;
+    double *x_out, *cost;
+    int *nit, *nfev, *status, *task;
+    double *acc, *att, *rates, *thrust;
+};
+
+template <int LANES, int TPL, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
+se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_constant__ SolveArgs A)
+{
+    extern __shared__ double smem_all[];
+    constexpr int GPB = BLOCK / LANES; /* problems (groups) per block */
+    const int gib = threadIdx.x / LANES;
+    double *sm = smem_all + gib * SM_DOUBLES;
+    const int N = P.horizon;
+    const long long stride = (long long)gridDim.x * GPB;
+    for (long long b = (long long)blockIdx.x * GPB + gib; b < A.B; b += stride) {
+        Solver<SubWarp<LANES>, TPL> sv(P, sm);
+        double p0[3], v0[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            p0[c] = __ldg(A.p0 + c * A.ld + b);
+            v0[c] = __ldg(A.v0 + c * A.ld + b);
+            sv.goal[c] = __ldg(A.goal + c * A.ld + b);
+        }
+        sv.has_goal = A.has_goal ? (A.has_goal[b] != 0) : true;
+        const bool warm = A.x_warm != nullptr && (A.warm_mask == nullptr || A.warm_mask[b] != 0);
+        if (warm) {
+            const double *xw = A.x_warm + b;
+            const long long ld = A.ld;
+            sv.warm_start(p0, v0, [xw, ld](int row) { return __ldg(xw + (long long)row * ld); });
+        } else
+            sv.cold_start(p0, v0);
+        SolveStats st;
+        sv.minimize(st);
+        if (A.x_out) {
+#pragma unroll
+            for (int tt = 0; tt < TPL; ++tt)
+                if (sv.act[tt]) {
+#pragma unroll
+                    for (int q = 0; q < 9; ++q)
+                        A.x_out[(long long)sv.row_of(tt, q) * A.ld + b] = sv.x[tt * 9 + q];
+                }
+        }
+        if (sv.grp.leader()) {
+            if (A.cost) A.cost[b] = st.f;
+            if (A.nit) A.nit[b] = st.nit;
+            if (A.nfev) A.nfev[b] = st.nfev;
+            if (A.status) A.status[b] = st.status;
+            if (A.task) A.task[b] = st.task;
+        }
+        if (A.acc || A.att || A.rates || A.thrust) {
+            const SolveArgs &a = A;
+            sv.extract([&a, b](int k, double ax, double ay, double az, double r0, double r1,
+                               double r2, double w0, double w1, double w2, double th) {
+                const long long ld = a.ld;
+                if (a.acc) {
+                    a.acc[(long long)(3 * k) * ld + b] = ax;
+                    a.acc[(long long)(3 * k + 1) * ld + b] = ay;
+                    a.acc[(long long)(3 * k + 2) * ld + b] = az;
+                }
+                if (a.att) {
+                    a.att[(long long)(3 * k) * ld + b] = r0;
+                    a.att[(long long)(3 * k + 1) * ld + b] = r1;
+                    a.att[(long long)(3 * k + 2) * ld + b] = r2;
+                }
+                if (a.rates) {
+                    a.rates[(long long)(3 * k) * ld + b] = w0;
+                    a.rates[(long long)(3 * k + 1) * ld + b] = w1;
+                    a.rates[(long long)(3 * k + 2) * ld + b] = w2;
+                }
+                if (a.thrust) a.thrust[(long long)k * ld + b] = th;
+            });
+        }
+        (void)N;
+    }
+}
+
+struct KernelChoice {
+    const void *fn;
+    int lanes, tpl, block;
+    int occ_blocks; /* resident blocks per SM (queried once) */
+    int regs;
+    bool ready;
+};
+
+constexpr int BLOCK = 128;
+
+template <int LANES, int TPL, int MINB>
+KernelChoice make_choice()
+{
+    KernelChoice k;
+    k.fn = (const void *)se3mpc_solve_kernel<LANES, TPL, BLOCK, MINB>;
+    k.lanes = LANES;
+    k.tpl = TPL;
+    k.block = BLOCK;
+    k.occ_blocks = 0;
+    k.regs = 0;
+    k.ready = false;
+    return k;
+}
+
+KernelChoice g_kernels[5] = {
+    make_choice<4, 1, 2>(), make_choice<8, 1, 2>(), make_choice<16, 1, 2>(),
+    make_choice<32, 1, 2>(), make_choice<32, 2, 2>(),
+};
+std::mutex g_mu;
+int g_sms = 0;
+
+int smem_bytes(const KernelChoice &k) { return (k.block / k.lanes) * SM_DOUBLES * (int)sizeof(double); }
+
+int set_err(cudaError_t e, const char *what)
+{
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return DART_E_CUDA;
+}
+
+KernelChoice *pick_kernel(int N)
+{
+    int idx = N <= 4 ? 0 : N <= 8 ? 1 : N <= 16 ? 2 : N <= 32 ? 3 : 4;
+    return &g_kernels[idx];
+}
+
+int prepare(KernelChoice *k)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (k->ready) return DART_OK;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        set_err(e, "cudaGetDevice");
+        return DART_E_NODEVICE;
+    }
+    if (g_sms == 0) {
+        e = cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return set_err(e, "cudaDeviceGetAttribute");
+    }
+    const int smem = smem_bytes(*k);
+    e = cudaFuncSetAttribute(k->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return set_err(e, "cudaFuncSetAttribute(smem)");
+    e = cudaFuncSetAttribute(k->fn, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+    if (e != cudaSuccess) return set_err(e, "cudaFuncSetAttribute(carveout)");
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, k->fn);
+    if (e != cudaSuccess) return set_err(e, "cudaFuncGetAttributes");
+    k->regs = fa.numRegs;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k->occ_blocks, k->fn, k->block, smem);
+    if (e != cudaSuccess) return set_err(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+    if (k->occ_blocks < 1) k->occ_blocks = 1;
+    k->ready = true;
+    return DART_OK;
+}
+
+int check_params(const dart_se3mpc_params *p)
+{
+    if (!p || p->struct_size != (int)sizeof(dart_se3mpc_params)) return DART_E_BADARG;
+    if (p->horizon < 1 || p->horizon > 64) return DART_E_UNSUPPORTED;
+    if (p->max_corrections < 1 || p->max_corrections > MMAX) return DART_E_UNSUPPORTED;
+    if (p->max_iterations < 0 || p->max_linesearch < 0) return DART_E_BADARG;
+    if (!(p->dt > 0.0) || !(p->mass > 0.0)) return DART_E_BADARG;
+    return DART_OK;
+}
+
+long long grid_for(const KernelChoice &k, long long B)
+{
+    const long long gpb = k.block / k.lanes;
+    long long need = (B + gpb - 1) / gpb;
+    long long cap = (long long)g_sms * k.occ_blocks;
+    return need < cap ? need : cap;
+}
+
+} /* namespace */
+
+extern "C" {
+
+int dart_abi_version(void) { return DART_SE3MPC_ABI_VERSION; }
+const char *dart_last_cuda_error(void) { return g_err; }
+int64_t dart_launch_count(void) { return (int64_t)g_launches.load(); }
+void dart_count_launch_(void) { g_launches.fetch_add(1); }
+
+void dart_se3mpc_default_params(dart_se3mpc_params *p)
+{
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->struct_size = (int)sizeof(*p);
+    p->horizon = 6;             /* se3_mpc_planner.py:41 */
+    p->max_iterations = 15;     /* :66 */
+    p->max_corrections = 10;    /* SciPy maxcor */
+    p->max_linesearch = 20;     /* SciPy maxls */
+    p->max_fun = 15000;         /* SciPy maxfun */
+    p->gradient_mode = 0;
+    p->dt = 1.0 / 400.0;        /* timing_alignment.py:76-78 with frozen_config.py:86 */
+    p->mass = 1.5;              /* :149 */
+    p->gravity = 9.81;          /* :150 */
+    p->pos_bound = 100.0;       /* :384 */
+    p->max_velocity = 10.0;     /* :45 */
+    p->max_thrust = 25.0;       /* :48 */
+    p->min_thrust = 2.0;        /* :49 */
+    p->tilt_thrust = 25.0 * 0.70710678118654746; /* max_thrust*sin(pi/4) (:393-397) */
+    p->w_pos = 100.0;           /* :56-59 */
+    p->w_vel = 10.0;
+    p->w_acc = 1.0;
+    p->w_thrust = 0.1;
+    p->gtol = 5e-2;             /* :68, :264 */
+    p->ftol = 5e-1;             /* :265 */
+}
+
+int dart_se3mpc_kernel_info(const dart_se3mpc_params *params, int64_t B, int32_t *lanes,
+                            int32_t *block_threads, int32_t *grid_blocks, int32_t *smem,
+                            int32_t *regs_per_thread)
+{
+    int rc = check_params(params);
+    if (rc) return rc;
+    KernelChoice *k = pick_kernel(params->horizon);
+    rc = prepare(k);
+    if (rc) return rc;
+    if (lanes) *lanes = k->lanes;
+    if (block_threads) *block_threads = k->block;
+    if (grid_blocks) *grid_blocks = (int32_t)grid_for(*k, B > 0 ? B : 1);
+    if (smem) *smem = smem_bytes(*k);
+    if (regs_per_thread) *regs_per_thread = k->regs;
+    return DART_OK;
+}
+
+int dart_se3mpc_solve_batch(const dart_se3mpc_params *params, int64_t B, int64_t ld,
+                            const double *p0, const double *v0, const double *goal,
+                            const uint8_t *has_goal, const double *x_warm,
+                            const uint8_t *warm_mask, double *x_out, double *cost, int32_t *nit,
+                            int32_t *nfev, int32_t *status, int32_t *task, double *acc,
+                            double *att, double *rates, double *thrust, void *cuda_stream)
+{
+    int rc = check_params(params);
+    if (rc) return rc;
+    if (B < 0 || ld < B || !p0 || !v0 || !goal) return DART_E_BADARG;
+    if (B == 0) return DART_OK;
+    KernelChoice *k = pick_kernel(params->horizon);
+    rc = prepare(k);
+    if (rc) return rc;
+    SolveArgs a;
+    a.B = B; a.ld = ld;
+    a.p0 = p0; a.v0 = v0; a.goal = goal; a.has_goal = has_goal;
+    a.x_warm = x_warm; a.warm_mask = warm_mask;
+    a.x_out = x_out; a.cost = cost; a.nit = nit; a.nfev = nfev; a.status = status; a.task = task;
+    a.acc = acc; a.att = att; a.rates = rates; a.thrust = thrust;
+    dart_se3mpc_params P = *params;
+    void *args[] = {(void *)&P, (void *)&a};
+    const long long grid = grid_for(*k, B);
+    cudaError_t e = cudaLaunchKernel(k->fn, dim3((unsigned)grid), dim3(k->block), args,
+                                     smem_bytes(*k), (cudaStream_t)cuda_stream);
+    if (e != cudaSuccess) return set_err(e, "cudaLaunchKernel(se3mpc_solve)");
+    g_launches.fetch_add(1);
+    return DART_OK;
+}
+
+/* ---- host-buffer entry: staged through a cached per-thread device workspace --------------- */
+namespace {
+struct HostWs {
+    void *dev = nullptr;
+    size_t cap = 0;
+    cudaStream_t stream = nullptr;
+};
+thread_local HostWs g_ws;
+}
+
+int dart_se3mpc_solve_batch_host(const dart_se3mpc_params *params, int64_t B,
+                                 const double *p0, const double *v0, const double *goal,
+                                 const uint8_t *has_goal, const double *x_warm, double *x_out,
+                                 double *cost, int32_t *nit, int32_t *nfev, int32_t *status,
+                                 double *acc, double *att, double *rates, double *thrust)
+{
+    int rc = check_params(params);
+    if (rc) return rc;
+    if (B < 0 || !p0 || !v0 || !goal) return DART_E_BADARG;
+    if (B == 0) return DART_OK;
+    const int N = params->horizon;
+    const size_t Bp = (size_t)((B + 31) / 32 * 32); /* padded row pitch */
+    /* rows of 8-byte elements: p0 3, v0 3, goal 3, x_warm 9N, x 9N, cost 1, acc/att/rates 3N each,
+     * thrust N; then int32 rows nit, nfev, status, task; then u8 has_goal */
+    const size_t drows = 9 + 9 * (size_t)N + 9 * (size_t)N + 1 + 9 * (size_t)N + (size_t)N;
+    const size_t bytes = drows * Bp * 8 + 4 * Bp * 4 + Bp;
+    cudaError_t e;
+    if (!g_ws.stream) {
+        e = cudaStreamCreateWithFlags(&g_ws.stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) return set_err(e, "cudaStreamCreate");
+    }
+    if (g_ws.cap < bytes) {
+        if (g_ws.dev) cudaFree(g_ws.dev);
+        g_ws.dev = nullptr;
+        g_ws.cap = 0;
+        e = cudaMalloc(&g_ws.dev, bytes);
+        if (e != cudaSuccess) return set_err(e, "cudaMalloc(workspace)");
+        g_ws.cap = bytes;
+    }
+    cudaStream_t s = g_ws.stream;
+    double *d = (double *)g_ws.dev;
+    double *d_p0 = d, *d_v0 = d_p0 + 3 * Bp, *d_goal = d_v0 + 3 * Bp, *d_xw = d_goal + 3 * Bp;
+    double *d_x = d_xw + 9 * (size_t)N * Bp, *d_cost = d_x + 9 * (size_t)N * Bp;
+    double *d_acc = d_cost + Bp, *d_att = d_acc + 3 * (size_t)N * Bp, *d_rates = d_att + 3 * (size_t)N * Bp;
+    double *d_thr = d_rates + 3 * (size_t)N * Bp;
+    int32_t *d_nit = (int32_t *)(d_thr + (size_t)N * Bp), *d_nfev = d_nit + Bp, *d_status = d_nfev + Bp,
+            *d_task = d_status + Bp;
+    uint8_t *d_hg = (uint8_t *)(d_task + Bp);
+#define H2D(dst, src, rows, esz)                                                              \
+    do {                                                                                      \
+        e = cudaMemcpy2DAsync(dst, Bp * (esz), src, (size_t)B * (esz), (size_t)B * (esz), rows, \
+                              cudaMemcpyHostToDevice, s);                                     \
+        if (e != cudaSuccess) return set_err(e, "cudaMemcpy2DAsync H2D");                     \
+    } while (0)
+#define D2H(dst, src, rows, esz)                                                              \
+    do {                                                                                      \
+        if (dst) {                                                                            \
+            e = cudaMemcpy2DAsync(dst, (size_t)B * (esz), src, Bp * (esz), (size_t)B * (esz), rows, \
+                                  cudaMemcpyDeviceToHost, s);                                 \
+            if (e != cudaSuccess) return set_err(e, "cudaMemcpy2DAsync D2H");                 \
+        }                                                                                     \
+    } while (0)
+    H2D(d_p0, p0, 3, 8);
+    H2D(d_v0, v0, 3, 8);
+    H2D(d_goal, goal, 3, 8);
+    if (has_goal) H2D(d_hg, has_goal, 1, 1);
+    if (x_warm) H2D(d_xw, x_warm, 9 * (size_t)N, 8);
+    rc = dart_se3mpc_solve_batch(params, B, (int64_t)Bp, d_p0, d_v0, d_goal, has_goal ? d_hg : nullptr,
+                                 x_warm ? d_xw : nullptr, nullptr, x_out ? d_x : nullptr,
+                                 cost ? d_cost : nullptr, nit ? d_nit : nullptr,
+                                 nfev ? d_nfev : nullptr, status ? d_status : nullptr, nullptr,
+                                 acc ? d_acc : nullptr, att ? d_att : nullptr,
+                                 rates ? d_rates : nullptr, thrust ? d_thr : nullptr, (void *)s);
+    if (rc) return rc;
+    D2H(x_out, d_x, 9 * (size_t)N, 8);
+    D2H(cost, d_cost, 1, 8);
+    D2H(nit, d_nit, 1, 4);
+    D2H(nfev, d_nfev, 1, 4);
+    D2H(status, d_status, 1, 4);
+    D2H(acc, d_acc, 3 * (size_t)N, 8);
+    D2H(att, d_att, 3 * (size_t)N, 8);
+    D2H(rates, d_rates, 3 * (size_t)N, 8);
+    D2H(thrust, d_thr, (size_t)N, 8);
+#undef H2D
+#undef D2H
+    e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return set_err(e, "cudaStreamSynchronize");
+    return DART_OK;
+}
+
+} /* extern "C" */

@@ -1,0 +1,153 @@
+/*
+ * dart_se3mpc.h -- C ABI of the B200-native batched SE(3)-MPC solve path.
+ *
+ * The reference (Pasqui1010/DART-Planner) is pure Python and has no FFI for this path; its
+ * seam is the class contract of `SE3MPCPlanner` (src/dart_planner/planning/se3_mpc_planner.py).
+ * Every entry point below names the reference interface it stands in for.  All pointers are
+ * caller-owned DEVICE memory unless a name ends in `_host`; layouts are batch-major
+ * structure-of-arrays: a quantity with C components for B problems is `[C][ld]` with the
+ * problem index contiguous (`ld >= B` is the row pitch in elements, so a rank can pass a
+ * slice of a larger allocation).  Calls are asynchronous on `cuda_stream` (a cudaStream_t),
+ * allocate nothing on the hot path, and return 0 or a negative DART_E_* code; they never
+ * throw.  Distinct (buffers, stream) pairs may be used concurrently.
+ */
+#ifndef DART_SE3MPC_H
+#define DART_SE3MPC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DART_SE3MPC_ABI_VERSION 1
+
+enum {
+    DART_OK = 0,
+    DART_E_BADARG = -1,      /* null pointer / negative size / struct_size mismatch        */
+    DART_E_UNSUPPORTED = -2, /* horizon > 64, max_corrections > 10, ...                    */
+    DART_E_CUDA = -3,        /* a CUDA runtime call failed; see dart_last_cuda_error()     */
+    DART_E_NODEVICE = -4
+};
+
+/* Termination codes written to `task` (SciPy task numbers in brackets,
+ * scipy/optimize/_lbfgsb_py.py as driven by se3_mpc_planner.py:256-268). */
+enum {
+    DART_TASK_CONV_PGTOL = 1,   /* [401] projected gradient <= gtol                        */
+    DART_TASK_CONV_FTOL = 2,    /* [402] relative reduction of f <= ftol                   */
+    DART_TASK_STOP_MAXITER = 3, /* [504] wrapper: n_iterations >= maxiter                  */
+    DART_TASK_STOP_MAXFUN = 4,  /* [502] wrapper: nfev > maxfun                            */
+    DART_TASK_ABNORMAL = 5      /* ABNORMAL: line search failed with no stored pairs       */
+};
+
+/* SE3MPCConfig (se3_mpc_planner.py:36-79) + the planner's hard-wired mass/gravity
+ * (:149-151) + SciPy's L-BFGS-B options as the reference passes them (:262-267). */
+typedef struct dart_se3mpc_params {
+    int32_t struct_size;       /* = sizeof(dart_se3mpc_params)                             */
+    int32_t horizon;           /* prediction_horizon N, 1..64                              */
+    int32_t max_iterations;    /* maxiter                                                  */
+    int32_t max_corrections;   /* SciPy maxcor, 1..10 (SciPy default 10)                   */
+    int32_t max_linesearch;    /* SciPy maxls (default 20)                                 */
+    int32_t max_fun;           /* SciPy maxfun (default 15000)                             */
+    int32_t gradient_mode;     /* 0: reference gradient (:552-580, inconsistent by design) */
+                               /* 1: exact gradient of :516-550 (extension, self-oracle)   */
+    int32_t reserved0;
+    double dt;                 /* effective planner dt (timing_alignment.py:76-78)         */
+    double mass, gravity;      /* 1.5 kg, 9.81 m/s^2 (:149-150)                            */
+    double pos_bound;          /* +-100 m (:384)                                           */
+    double max_velocity;       /* (:388)                                                   */
+    double tilt_thrust;        /* max_thrust*sin(max_tilt_angle) (:393-397)                */
+    double min_thrust, max_thrust; /* (:400)                                               */
+    double w_pos, w_vel, w_acc, w_thrust; /* cost weights (:56-59)                          */
+    double gtol;               /* convergence_tolerance (:264)                             */
+    double ftol;               /* 10*convergence_tolerance (:265)                          */
+} dart_se3mpc_params;
+
+int dart_abi_version(void);
+const char *dart_last_cuda_error(void);
+
+/* Fills `p` with the reference's defaults (SE3MPCConfig dataclass defaults, effective
+ * dt = 1/400 s, SciPy option defaults). */
+void dart_se3mpc_default_params(dart_se3mpc_params *p);
+
+/*
+ * Batched replacement of SE3MPCPlanner._solve_se3_mpc (se3_mpc_planner.py:230-280):
+ * initial guess (:282-359), bounds (:378-402), L-BFGS-B on (:516-550, :552-580), and the
+ * solution extraction (:582-654), for B independent problems.
+ *
+ * inputs   p0, v0, goal : [3][ld]   current position / velocity, goal position
+ *          has_goal     : [ld] u8 or NULL (all problems have a goal)           (:341, :523)
+ *          x_warm       : [9N][ld] previous solution or NULL (cold start)       (:294-327)
+ *          warm_mask    : [ld] u8 or NULL (all warm when x_warm != NULL)
+ * outputs  x_out        : [9N][ld]  rows in the reference's packed order [P | V | T] (:361-376)
+ *          cost         : [ld]      OptimizeResult.fun
+ *          nit,nfev,status,task : [ld] int32 (status as OptimizeResult.status: 0/1/2)
+ *          acc, att, rates : [3N][ld] rows 3k+c; thrust : [N][ld]                (:582-654)
+ *          any output pointer may be NULL (not written).
+ */
+int dart_se3mpc_solve_batch(const dart_se3mpc_params *params, int64_t B, int64_t ld,
+                            const double *p0, const double *v0, const double *goal,
+                            const uint8_t *has_goal, const double *x_warm,
+                            const uint8_t *warm_mask, double *x_out, double *cost, int32_t *nit,
+                            int32_t *nfev, int32_t *status, int32_t *task, double *acc,
+                            double *att, double *rates, double *thrust, void *cuda_stream);
+
+/* Same call with every buffer in HOST memory (pageable or pinned): stages through an
+ * internal per-thread device workspace, copies in, solves, copies back and synchronises.
+ * This is the plugin-level entry the drop-in planner's single-problem `plan()` uses. */
+int dart_se3mpc_solve_batch_host(const dart_se3mpc_params *params, int64_t B,
+                                 const double *p0_host, const double *v0_host,
+                                 const double *goal_host, const uint8_t *has_goal_host,
+                                 const double *x_warm_host, double *x_out_host,
+                                 double *cost_host, int32_t *nit_host, int32_t *nfev_host,
+                                 int32_t *status_host, double *acc_host, double *att_host,
+                                 double *rates_host, double *thrust_host);
+
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+int64_t dart_launch_count(void);
+
+/* Name, registers and launch geometry of the solve kernel chosen for (horizon, B). */
+int dart_se3mpc_kernel_info(const dart_se3mpc_params *params, int64_t B, int32_t *lanes,
+                            int32_t *block_threads, int32_t *grid_blocks, int32_t *smem_bytes,
+                            int32_t *regs_per_thread);
+
+/* FP64 FMA throughput probe (bench.py's compute-roofline denominator): launches
+ * 148*8 blocks x 256 threads, each running 8 independent DFMA chains of `iters` steps;
+ * flops = threads * 8 * iters * 2.  `scratch`: >= 8 bytes of device memory. */
+int dart_fp64_probe(int32_t iters, int32_t *threads_out, double *scratch, void *cuda_stream);
+
+/* ---- occupancy grid (perception/explicit_geometric_mapper.py) on a dense device grid ----
+ * occ: float32 [nz][ny][nx] (x fastest); voxel key (kx,ky,kz) = floor(p/res) lives at index
+ * (kx-ox, ky-oy, kz-oz); keys outside the grid read `prior` (the reference's dict miss, :168). */
+typedef struct dart_grid {
+    int32_t nx, ny, nz;
+    int32_t ox, oy, oz;
+    double resolution;
+    double prior;
+    const float *occ;
+} dart_grid;
+
+/* query_occupancy_batch (:171-182): pos [3][ld] -> occ_out [ld] (float64 like the reference) */
+int dart_map_query_batch(const dart_grid *g, int64_t B, int64_t ld, const double *pos,
+                         double *occ_out, void *cuda_stream);
+/* is_trajectory_safe (:195-219, stencil :338-351) for B trajectories of npos points:
+ * positions [3*npos][ld] rows 3k+c  ->  first_hit [ld] int32 (-1 = safe) */
+int dart_map_traj_safe_batch(const dart_grid *g, int64_t B, int64_t ld, int32_t npos,
+                             const double *positions, double margin, double threshold,
+                             int32_t *first_hit, void *cuda_stream);
+/* _trace_ray (:250-309) for B rays: start, dir [3][ld], dist [ld] -> count [ld] voxels
+ * visited; if voxels != NULL the first min(count,max_vox) keys are written to
+ * voxels [max_vox][3][ld] int32. */
+int dart_map_trace_ray_batch(double resolution, int64_t B, int64_t ld, const double *start,
+                             const double *dir, const double *dist, int32_t max_vox,
+                             int32_t *count, int32_t *voxels, void *cuda_stream);
+/* add_obstacle (:399-423): rasterise n spheres (centres [3][n], radii [n]) into a writable
+ * grid with the reference's voxel-corner distance test; value 0.9. */
+int dart_map_add_spheres(const dart_grid *g, float *occ_writable, int32_t n,
+                         const double *centers, const double *radii, float value,
+                         void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DART_SE3MPC_H */

@@ -1,0 +1,62 @@
+/*
+ * tests/emu/emu_solver.cpp -- TEST INFRASTRUCTURE.
+ * Compiles dart_planner_b200/csrc/se3mpc_core.cuh for the HOST with a one-lane group so the
+ * CPU-only test tier can check the kernel's control flow against the oracle without a GPU.
+ * The product never loads this library (the product path is CUDA only).
+ */
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../dart_planner_b200/csrc/se3mpc_core.cuh"
+
+using namespace dartb200;
+
+template <int TPL>
+static void solve_one(const dart_se3mpc_params &P, const double *p0, const double *v0,
+                      const double *goal, int has_goal, const double *xw, double *x_out,
+                      double *acc, double *att, double *rates, double *thrust, SolveStats &st)
+{
+    double smem[SM_DOUBLES];
+    for (int i = 0; i < SM_DOUBLES; ++i) smem[i] = 0.0 / 0.0; /* NaN-poison: catches stale reads */
+    Solver<SeqGroup, TPL> sv(P, smem);
+    const int N = P.horizon;
+    sv.has_goal = has_goal != 0;
+    for (int c = 0; c < 3; ++c) sv.goal[c] = goal[c];
+    if (xw)
+        sv.warm_start(p0, v0, [&](int row) { return xw[row]; });
+    else
+        sv.cold_start(p0, v0);
+    sv.minimize(st);
+    for (int k = 0; k < N; ++k)
+        for (int q = 0; q < 9; ++q) x_out[(q / 3) * 3 * N + 3 * k + q % 3] = sv.x[k * 9 + q];
+    sv.extract([&](int k, double ax, double ay, double az, double a0, double a1, double a2,
+                   double w0, double w1, double w2, double th) {
+        acc[3 * k] = ax; acc[3 * k + 1] = ay; acc[3 * k + 2] = az;
+        att[3 * k] = a0; att[3 * k + 1] = a1; att[3 * k + 2] = a2;
+        rates[3 * k] = w0; rates[3 * k + 1] = w1; rates[3 * k + 2] = w2;
+        thrust[k] = th;
+    });
+}
+
+extern "C" int emu_solve_batch(const dart_se3mpc_params *P, long B, const double *p0,
+                               const double *v0, const double *goal, const unsigned char *has_goal,
+                               const double *x_warm, double *x, double *cost, int *nit, int *nfev,
+                               int *status, int *task, double *acc, double *att, double *rates,
+                               double *thrust)
+{
+    const int N = P->horizon, n = 9 * N;
+    if (N < 1 || N > 32 || P->max_corrections < 1 || P->max_corrections > MMAX) return -2;
+    for (long b = 0; b < B; ++b) {
+        SolveStats st;
+        const double *xw = x_warm ? x_warm + (long)n * b : nullptr;
+        const int hg = has_goal ? has_goal[b] : 1;
+#define CALL(T) solve_one<T>(*P, p0 + 3 * b, v0 + 3 * b, goal + 3 * b, hg, xw, x + (long)n * b, \
+                             acc + 3L * N * b, att + 3L * N * b, rates + 3L * N * b, thrust + (long)N * b, st)
+        if (N <= 8) CALL(8);
+        else if (N <= 20) CALL(20);
+        else CALL(32);
+#undef CALL
+        cost[b] = st.f; nit[b] = st.nit; nfev[b] = st.nfev; status[b] = st.status; task[b] = st.task;
+    }
+    return 0;
+}

@@ -1,0 +1,71 @@
+"""Mapper kernels against fixtures produced by the reference's ExplicitGeometricMapper and
+against the oracle at scale -- exact integer parity."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def test_trace_ray_fixtures():
+    import dart_planner_b200 as dp
+    d = load_golden("mapper")
+    g = dp.DenseOccupancyGrid((8, 8, 8), (0, 0, 0), 0.5)
+    v = g._trace_ray([0, 0, 0], np.array([1, 1, 0]) / np.sqrt(2), 5.0)
+    assert v == [tuple(r) for r in d["kat1"].tolist()]
+    assert all(sum(abs(a - b) for a, b in zip(p, q)) == 1 for p, q in zip(v, v[1:]))
+    v = g._trace_ray([0.3, -0.2, 1.1], [-1.0, 2.0, 0.5], 3.0)
+    assert v == [tuple(r) for r in d["kat2"].tolist()]
+    g2 = dp.DenseOccupancyGrid((8, 8, 8), (0, 0, 0), float(d["ray_res"]))
+    count, vox = g2.trace_rays(d["ray_start"], d["ray_dir"], d["ray_dist"], max_vox=int(d["ray_len"].max()))
+    count = count.cpu().numpy(); vox = vox.cpu().numpy()
+    np.testing.assert_array_equal(count, d["ray_len"])
+    off = 0
+    for i, L in enumerate(d["ray_len"]):
+        np.testing.assert_array_equal(vox[:L, :, i], d["ray_vox"][off:off + L])
+        off += L
+
+
+def test_sphere_query_safety_fixtures():
+    import dart_planner_b200 as dp
+    d = load_golden("mapper")
+    g = dp.DenseOccupancyGrid((256, 256, 256), (-128, -128, -128), 0.2)
+    g.add_obstacle([15.0, 5.0, 5.0], 2.0)
+    assert int((g.occ > 0.6).sum()) == int(d["kat3_nvox"]) == 4163
+    np.testing.assert_allclose(g.query_occupancy_batch(d["kat3_q"]).cpu().numpy(), d["kat3_occ"], atol=1e-7)
+    assert g.is_trajectory_safe(d["kat3_traj"], 1.5, 0.6) == (False, 4)
+    g = dp.DenseOccupancyGrid((128, 128, 128), (-64, -64, -64), 0.2)
+    g.add_obstacles(d["sph_c"], d["sph_r"])
+    np.testing.assert_allclose(g.query_occupancy_batch(d["sph_q"]).cpu().numpy(), d["sph_occ"], atol=1e-7)
+    idx = g.are_trajectories_safe(d["sph_traj"], 1.5, 0.6).cpu().numpy()
+    np.testing.assert_array_equal(idx, d["sph_idx"])
+    np.testing.assert_array_equal((idx < 0).astype(np.int32), d["sph_safe"])
+
+
+def test_config3_map_against_oracle(oracle_mod):
+    """BASELINE configs[2] map: 256^3 @ 0.2 m, 64 spheres (seed 2); 65 536 random queries, rays
+    and 8-point trajectories against the oracle."""
+    import dart_planner_b200 as dp
+    rng = np.random.default_rng(2)
+    cs, rs = rng.uniform(-20, 20, (64, 3)), rng.uniform(0.5, 2.0, 64)
+    g = dp.DenseOccupancyGrid((256, 256, 256), (-128, -128, -128), 0.2)
+    g.add_obstacles(cs, rs)
+    og = oracle_mod.DenseGrid((256, 256, 256), (-128, -128, -128), 0.2)
+    for c, r in zip(cs, rs):
+        og.add_sphere(c, float(r))
+    np.testing.assert_array_equal(g.occ.cpu().numpy(), og.occ)
+    q = rng.uniform(-27, 27, (4096, 3))                      # includes out-of-grid points
+    np.testing.assert_array_equal(g.query_occupancy_batch(q).cpu().numpy(), og.query(q))
+    trajs = rng.uniform(-20, 20, (2048, 1, 3)) + np.cumsum(rng.normal(0, 0.6, (2048, 8, 3)), axis=1)
+    idx = g.are_trajectories_safe(trajs, 1.5, 0.6).cpu().numpy()
+    want = np.array([og.traj_safe(t, 1.5, 0.6) for t in trajs])
+    np.testing.assert_array_equal(idx, want)
+    assert (want >= 0).any() and (want < 0).any()
+    starts = rng.uniform(-20, 20, (2048, 3)); dirs = rng.normal(0, 1, (2048, 3)); dist = rng.uniform(0.1, 20, 2048)
+    count, vox = g.trace_rays(starts, dirs, dist, max_vox=256)
+    count, vox = count.cpu().numpy(), vox.cpu().numpy()
+    for i in range(0, 2048, 8):
+        v, n = oracle_mod.trace_ray(0.2, starts[i], dirs[i], dist[i], max_vox=256)
+        assert n == count[i]
+        np.testing.assert_array_equal(vox[:n, :, i], v)

@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- batched SE(3)-MPC solves/sec on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch B]
+
+A "step" is one batched solve of the workload (BASELINE.json configs[1]: 4096 hover-to-goal
+problems, seed 1, p0~U(-10,10)^3, v0=0, goal~U(-15,15)^2 x U(3,8), default airframe, N=8,
+dt=0.1 from config/defaults.yaml) per GPU.  `value` times the solve kernel on HBM-resident
+inputs; `e2e` times the same call from pinned HOST buffers (H2D + kernel + D2H of every
+output) through the package's public BatchWorkspace API.  One JSON line on stdout (rank 0).
+
+`--impl reference` times the CPU restatement of the reference path (oracle/, C, all host
+threads) on the same workload; that and the `cpu_baseline` leg are the only places this file
+touches oracle/.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "batched SE(3)-MPC solves/sec"
+UNIT = "solves/s"
+L2_FLUSH_BYTES = 256 << 20
+
+
+def workload_inputs(B, seed):
+    """SURVEY.md 8(d) config 2 distribution (reference experiments/validation/benchmark_audit_improvements.py:292-302)."""
+    rng = np.random.default_rng(seed)
+    p0 = rng.uniform(-10, 10, (B, 3))
+    v0 = np.zeros((B, 3))
+    goal = np.concatenate([rng.uniform(-15, 15, (B, 2)), rng.uniform(3, 8, (B, 1))], axis=1)
+    return p0, v0, goal
+
+
+def alg_bytes_per_solve(N):
+    """inputs 9 fp64 + outputs (19N+1) fp64 + 3 int32 (+1 int32 task code)."""
+    return 8 * 9 + 8 * (19 * N + 1) + 4 * 4
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed regions run."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self.active = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            if self.active.is_set():
+                try:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    try:
+                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+            time.sleep(0.002)
+
+    def stop(self):
+        self._stop.set()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def run_reference(args):
+    """CPU arm: the oracle port of the reference path on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    B, N = args.batch, args.horizon
+    cores = host_cores()
+    params = oracle.make_params(horizon=N, dt=args.dt)
+    p0, v0, goal = workload_inputs(B, 1)
+    for _ in range(args.warmup):
+        oracle.solve_batch(params, p0, v0, goal, nthreads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.solve_batch(params, p0, v0, goal, nthreads=cores)
+    dt = time.perf_counter() - t0
+    value = args.steps * B / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} passes over the {B}-problem workload, oracle/ C port of "
+                                   "se3_mpc_planner.py + L-BFGS-B, pthreads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": f"{args.batch} batched hover-to-goal SE(3)-MPC solves per GPU (BASELINE configs[1]): "
+                        f"seed 1, p0~U(-10,10)^3, v0=0, goal~U(-15,15)^2xU(3,8), default airframe m=1.5 kg",
+            "batch_per_gpu": args.batch, "horizon": args.horizon, "dt": args.dt,
+            "max_iterations": 15, "convergence_tolerance": 0.05, "gradient": "reference (:552-580)",
+            "parallelism": f"dp{args.gpus} by problem index, replicated params, no collective in the solve",
+            "l2": f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)"}
+
+
+def time_steps(torch, fn, flush, steps, warmup, stream):
+    """K timed steps, each bracketed by CUDA events on the launching stream, L2 flushed in
+    between (outside the event pairs).  Returns summed milliseconds."""
+    for _ in range(warmup):
+        flush.zero_()
+        fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in evs:
+        flush.zero_()
+        a.record(stream)
+        fn()
+        b.record(stream)
+    torch.cuda.synchronize()
+    return [a.elapsed_time(b) for a, b in evs]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="problems per GPU per step")
+    ap.add_argument("--horizon", type=int, default=8)
+    ap.add_argument("--dt", type=float, default=0.1)
+    ap.add_argument("--no-extras", action="store_true", help="skip sweep / latency / cpu baseline legs")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: dart_planner_b200 has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import ctypes as C
+    import dart_planner_b200 as dp
+    from dart_planner_b200 import _cabi
+    from dart_planner_b200.config import make_params
+    from dart_planner_b200.planner import BatchWorkspace
+
+    L = _cabi.lib()
+    cfg = dp.SE3MPCConfig(prediction_horizon=args.horizon, dt=args.dt)
+    params = make_params(cfg)
+    B, N = args.batch, args.horizon
+    p0, v0, goal = workload_inputs(B, 1 + 1000 * rank)
+    ws = BatchWorkspace(params, B, pinned=True, outputs="all")
+    ws.set_inputs_device(p0, v0, goal)
+    ws.stage_host_inputs(p0, v0, goal)
+    stream = torch.cuda.current_stream()
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    # ---- value: kernel on resident inputs ------------------------------------------------
+    barrier()
+    n0 = L.dart_launch_count()
+    sampler.active.set()
+    ms = time_steps(torch, lambda: ws.solve_device(stream), flush, args.steps, args.warmup, stream)
+    sampler.active.clear()
+    launches = L.dart_launch_count() - n0 - args.warmup
+    barrier()
+    total_ms = float(sum(ms))
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = world * B * args.steps / (total_ms_max * 1e-3)
+
+    # ---- e2e: pinned host -> device -> solve -> pinned host -------------------------------
+    barrier()
+    sampler.active.set()
+    ms_e2e = time_steps(torch, lambda: ws.solve_staged(stream), flush, args.steps, args.warmup, stream)
+    sampler.active.clear()
+    barrier()
+    t = torch.tensor([float(sum(ms_e2e))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / (float(t.item()) * 1e-3)
+
+    if rank != 0:
+        sampler.stop()
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the solve kernel (rank 0) ----------------------------------------------
+    hbm_peak, peak_src = load_peaks()
+    kernel_ms = statistics.mean(ms)
+    ab = alg_bytes_per_solve(N) * B
+    achieved_gbs = ab / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "alg_bytes_per_solve": alg_bytes_per_solve(N), "kernel_ms": kernel_ms,
+                "kernel": "se3mpc_solve_kernel"}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            with open(traffic_file) as fh:
+                tf = json.load(fh)
+            roofline["traffic"] = tf.get(f"B{B}_N{N}", {}).get("dram_bytes_per_launch")
+            roofline["traffic_source"] = tf.get("source")
+        except Exception:
+            pass
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": ws.h2d_bytes,
+                "d2h_bytes_per_step": ws.d2h_bytes, "ms_per_step": float(sum(ms_e2e)) / args.steps,
+                "api": "dart_planner_b200.planner.BatchWorkspace.solve_staged (pinned host buffers)"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+    }
+    info = [C.c_int32() for _ in range(5)]
+    if L.dart_se3mpc_kernel_info(C.byref(params), B, *[C.byref(i) for i in info]) == 0:
+        line["kernel_info"] = {"lanes_per_problem": info[0].value, "block": info[1].value,
+                               "grid": info[2].value, "smem_bytes": info[3].value,
+                               "regs_per_thread": info[4].value}
+
+    if world == 1 and not args.no_extras:
+        # FP64 FMA peak probe (compute-roofline denominator)
+        scratch = torch.zeros(8, dtype=torch.float64, device="cuda")
+        th = C.c_int32()
+        iters = 1 << 16
+        for _ in range(2):
+            L.dart_fp64_probe(iters, C.byref(th), scratch.data_ptr(), stream.cuda_stream)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.active.set()
+        a.record(stream)
+        L.dart_fp64_probe(iters, C.byref(th), scratch.data_ptr(), stream.cuda_stream)
+        b.record(stream)
+        torch.cuda.synchronize()
+        sampler.active.clear()
+        fp64_peak = th.value * 8.0 * iters * 2.0 / (a.elapsed_time(b) * 1e-3) / 1e12
+        # CPU baseline + algorithmic flops from the instrumented oracle on the same batch
+        import oracle
+        cores = host_cores()
+        oparams = oracle.make_params(horizon=N, dt=args.dt)
+        r1 = oracle.solve_batch(oparams, p0, v0, goal, nthreads=cores)
+        t0 = time.perf_counter()
+        reps = 0
+        while time.perf_counter() - t0 < 10.0:
+            oracle.solve_batch(oparams, p0, v0, goal, nthreads=cores)
+            reps += 1
+        cpu_dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {
+            "value": reps * B / cpu_dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{reps} passes over the same {B}-problem workload (~10 s), oracle/ C port of "
+                      "se3_mpc_planner.py + SciPy L-BFGS-B semantics, pthreads"}
+        flops_per_solve = r1.flops / B
+        ach_tf = flops_per_solve * B / (kernel_ms * 1e-3) / 1e12
+        roofline["fp64"] = {"achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                            "frac": ach_tf / fp64_peak, "alg_flops_per_solve": flops_per_solve,
+                            "peak_source": "DFMA probe kernel measured in this run"}
+        # parity of the timed configuration against the oracle (reported, not timed)
+        sol = ws.solve_device(stream).numpy()
+        relf = np.abs(sol.cost - r1.cost) / np.maximum(np.abs(r1.cost), 1.0)
+        line["parity"] = {
+            "vs": "oracle (pinned to the reference by tests/golden)",
+            "max_rel_cost_err": float(relf.max()), "max_abs_x_err": float(np.abs(sol.x - r1.x).max()),
+            "counter_agreement": float(((sol.nit == r1.nit) & (sol.nfev == r1.nfev) & (sol.status == r1.status)).mean()),
+            "nit_hist": np.bincount(sol.nit, minlength=4).tolist()}
+        # larger batches (same distribution): throughput once the machine is full
+        sweep = {}
+        for Bs in (65536, 1 << 20):
+            w2 = BatchWorkspace(params, Bs, pinned=True, outputs="all")
+            a0, b0, c0 = workload_inputs(Bs, 2)
+            w2.set_inputs_device(a0, b0, c0)
+            w2.stage_host_inputs(a0, b0, c0)
+            sampler.active.set()
+            m1 = time_steps(torch, lambda: w2.solve_device(stream), flush, 10, 3, stream)
+            m2 = time_steps(torch, lambda: w2.solve_staged(stream), flush, 5, 3, stream)
+            sampler.active.clear()
+            k_ms = statistics.mean(m1)
+            sweep[f"B{Bs}"] = {"value": Bs / (k_ms * 1e-3), "kernel_ms": k_ms,
+                               "hbm_frac": alg_bytes_per_solve(N) * Bs / (k_ms * 1e-3) / 1e9 / hbm_peak,
+                               "fp64_frac": flops_per_solve * Bs / (k_ms * 1e-3) / 1e12 / fp64_peak,
+                               "e2e_value": Bs / (statistics.mean(m2) * 1e-3)}
+            del w2
+        line["sweep"] = sweep
+        # single-solve latency through the drop-in planner (metric's second half)
+        planner = dp.SE3MPCPlanner.from_yaml()
+        st = dp.DroneState(0.0, np.array([0.0, 0.0, 2.0]))
+        planner.set_goal(np.array([10.0, 0.0, 5.0]))
+        lat = []
+        for i in range(260):
+            t0 = time.perf_counter()
+            planner.plan(st)
+            lat.append((time.perf_counter() - t0) * 1e3)
+        lat = lat[60:]
+        line["single_solve_latency_ms"] = {"p50": statistics.median(lat), "p95": sorted(lat)[int(0.95 * len(lat))],
+                                           "api": "SE3MPCPlanner.plan (host in, host out)", "n": len(lat)}
+    sampler.stop()
+    line["clocks"] = sampler.summary()
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

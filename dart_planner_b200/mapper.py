@@ -92,8 +92,8 @@ class DenseOccupancyGrid:
         BatchSolution.out) -> (ld,) int32 first-collision index, -1 = safe."""
         torch = _torch()
         ld = positions_soa.shape[1]
-        assert positions_soa.is_cuda and positions_soa.dtype == torch.float64 and positions_soa.stride(1) == 1
-        assert positions_soa.stride(0) == ld and positions_soa.shape[0] >= 3 * npos
+        assert positions_soa.is_cuda and positions_soa.dtype == torch.float64 and positions_soa.is_contiguous()
+        assert positions_soa.shape[0] >= 3 * npos
         if out is None:
             out = torch.empty(ld, dtype=torch.int32, device=self.device)
         g = self._grid()

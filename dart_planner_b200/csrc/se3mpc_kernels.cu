@@ -8,6 +8,7 @@
  */
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -107,7 +108,7 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
 
 struct KernelChoice {
     const void *fn;
-    int lanes, tpl, block;
+    int lanes, tpl, block, minb;
     int occ_blocks; /* resident blocks per SM (queried once) */
     int regs;
     bool ready;
@@ -115,23 +116,27 @@ struct KernelChoice {
 
 constexpr int BLOCK = 128;
 
-template <int LANES, int TPL, int MINB>
+template <int LANES, int TPL, int MINB, int BLK = BLOCK>
 KernelChoice make_choice()
 {
     KernelChoice k;
-    k.fn = (const void *)se3mpc_solve_kernel<LANES, TPL, BLOCK, MINB>;
+    k.fn = (const void *)se3mpc_solve_kernel<LANES, TPL, BLK, MINB>;
     k.lanes = LANES;
     k.tpl = TPL;
-    k.block = BLOCK;
+    k.block = BLK;
+    k.minb = MINB;
     k.occ_blocks = 0;
     k.regs = 0;
     k.ready = false;
     return k;
 }
 
-KernelChoice g_kernels[5] = {
+KernelChoice g_kernels[] = {
     make_choice<4, 1, 2>(), make_choice<8, 1, 2>(), make_choice<16, 1, 2>(),
     make_choice<32, 1, 2>(), make_choice<32, 2, 2>(),
+    /* tuning variants, selected with DART_SE3MPC_VARIANT=<index> (tools/kbench.py) */
+    make_choice<4, 2, 2>(), make_choice<8, 1, 3>(), make_choice<8, 1, 4>(), make_choice<8, 1, 4, 64>(),
+    make_choice<8, 1, 8, 64>(),
 };
 std::mutex g_mu;
 int g_sms = 0;
@@ -147,6 +152,11 @@ int set_err(cudaError_t e, const char *what)
 KernelChoice *pick_kernel(int N)
 {
     int idx = N <= 4 ? 0 : N <= 8 ? 1 : N <= 16 ? 2 : N <= 32 ? 3 : 4;
+    if (const char *v = getenv("DART_SE3MPC_VARIANT")) {
+        const int want = atoi(v);
+        const int nk = (int)(sizeof(g_kernels) / sizeof(g_kernels[0]));
+        if (want >= 0 && want < nk && g_kernels[want].lanes * g_kernels[want].tpl >= N) idx = want;
+    }
     return &g_kernels[idx];
 }
 
@@ -167,7 +177,11 @@ int prepare(KernelChoice *k)
     const int smem = smem_bytes(*k);
     e = cudaFuncSetAttribute(k->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_err(e, "cudaFuncSetAttribute(smem)");
-    e = cudaFuncSetAttribute(k->fn, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+    /* shared-memory share of the 256 KB L1: what `minb` resident blocks need (+1 KB each that
+     * the driver reserves); the rest stays L1 for the per-lane S/Y pairs in local memory */
+    int carve = (int)((long long)k->minb * (smem + 1024) * 100 / (228 * 1024)) + 1;
+    if (carve > 100) carve = 100;
+    e = cudaFuncSetAttribute(k->fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     if (e != cudaSuccess) return set_err(e, "cudaFuncSetAttribute(carveout)");
     cudaFuncAttributes fa;
     e = cudaFuncGetAttributes(&fa, k->fn);

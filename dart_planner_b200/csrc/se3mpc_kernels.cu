@@ -34,7 +34,7 @@ struct SolveArgs {
     double *acc, *att, *rates, *thrust;
 };
 
-template <int LANES, int TPL, int BLOCK, int MINB>
+template <int LANES, int TPL, int BLOCK, int MINB, int GM>
 __global__ void __launch_bounds__(BLOCK, MINB)
 se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_constant__ SolveArgs A)
 {
@@ -44,8 +44,9 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
     double *sm = smem_all + gib * SM_DOUBLES;
     const int N = P.horizon;
     const long long stride = (long long)gridDim.x * GPB;
+    double ws[MMAX][9 * TPL], wy[MMAX][9 * TPL]; /* per-lane S / Y pairs (local memory, L1) */
     for (long long b = (long long)blockIdx.x * GPB + gib; b < A.B; b += stride) {
-        Solver<SubWarp<LANES>, TPL> sv(P, sm);
+        Solver<SubWarp<LANES>, TPL, GM> sv(P, sm, ws, wy);
         double p0[3], v0[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -107,7 +108,8 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
 }
 
 struct KernelChoice {
-    const void *fn;
+    const void *fn;       /* gradient_mode 0: the reference gradient (:552-580) */
+    const void *fn_exact; /* gradient_mode 1: exact gradient of :516-550       */
     int lanes, tpl, block, minb;
     int occ_blocks; /* resident blocks per SM (queried once) */
     int regs;
@@ -120,7 +122,8 @@ template <int LANES, int TPL, int MINB, int BLK = BLOCK>
 KernelChoice make_choice()
 {
     KernelChoice k;
-    k.fn = (const void *)se3mpc_solve_kernel<LANES, TPL, BLK, MINB>;
+    k.fn = (const void *)se3mpc_solve_kernel<LANES, TPL, BLK, MINB, 0>;
+    k.fn_exact = (const void *)se3mpc_solve_kernel<LANES, TPL, BLK, MINB, 1>;
     k.lanes = LANES;
     k.tpl = TPL;
     k.block = BLK;
@@ -175,14 +178,18 @@ int prepare(KernelChoice *k)
         if (e != cudaSuccess) return set_err(e, "cudaDeviceGetAttribute");
     }
     const int smem = smem_bytes(*k);
-    e = cudaFuncSetAttribute(k->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return set_err(e, "cudaFuncSetAttribute(smem)");
+    for (const void *fn : {k->fn, k->fn_exact}) {
+        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return set_err(e, "cudaFuncSetAttribute(smem)");
+    }
     /* shared-memory share of the 256 KB L1: what `minb` resident blocks need (+1 KB each that
      * the driver reserves); the rest stays L1 for the per-lane S/Y pairs in local memory */
     int carve = (int)((long long)k->minb * (smem + 1024) * 100 / (228 * 1024)) + 1;
     if (carve > 100) carve = 100;
-    e = cudaFuncSetAttribute(k->fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-    if (e != cudaSuccess) return set_err(e, "cudaFuncSetAttribute(carveout)");
+    for (const void *fn : {k->fn, k->fn_exact}) {
+        e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        if (e != cudaSuccess) return set_err(e, "cudaFuncSetAttribute(carveout)");
+    }
     cudaFuncAttributes fa;
     e = cudaFuncGetAttributes(&fa, k->fn);
     if (e != cudaSuccess) return set_err(e, "cudaFuncGetAttributes");
@@ -288,7 +295,8 @@ int dart_se3mpc_solve_batch(const dart_se3mpc_params *params, int64_t B, int64_t
     dart_se3mpc_params P = *params;
     void *args[] = {(void *)&P, (void *)&a};
     const long long grid = grid_for(*k, B);
-    cudaError_t e = cudaLaunchKernel(k->fn, dim3((unsigned)grid), dim3(k->block), args,
+    const void *fn = params->gradient_mode == 1 ? k->fn_exact : k->fn;
+    cudaError_t e = cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(k->block), args,
                                      smem_bytes(*k), (cudaStream_t)cuda_stream);
     if (e != cudaSuccess) return set_err(e, "cudaLaunchKernel(se3mpc_solve)");
     g_launches.fetch_add(1);

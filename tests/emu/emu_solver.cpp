@@ -11,14 +11,15 @@
 
 using namespace dartb200;
 
-template <int TPL>
+template <int TPL, int GM>
 static void solve_one(const dart_se3mpc_params &P, const double *p0, const double *v0,
                       const double *goal, int has_goal, const double *xw, double *x_out,
                       double *acc, double *att, double *rates, double *thrust, SolveStats &st)
 {
     double smem[SM_DOUBLES];
     for (int i = 0; i < SM_DOUBLES; ++i) smem[i] = 0.0 / 0.0; /* NaN-poison: catches stale reads */
-    Solver<SeqGroup, TPL> sv(P, smem);
+    static double ws[MMAX][9 * TPL], wy[MMAX][9 * TPL];
+    Solver<SeqGroup, TPL, GM> sv(P, smem, ws, wy);
     const int N = P.horizon;
     sv.has_goal = has_goal != 0;
     for (int c = 0; c < 3; ++c) sv.goal[c] = goal[c];
@@ -50,12 +51,14 @@ extern "C" int emu_solve_batch(const dart_se3mpc_params *P, long B, const double
         SolveStats st;
         const double *xw = x_warm ? x_warm + (long)n * b : nullptr;
         const int hg = has_goal ? has_goal[b] : 1;
-#define CALL(T) solve_one<T>(*P, p0 + 3 * b, v0 + 3 * b, goal + 3 * b, hg, xw, x + (long)n * b, \
+#define CALL1(T, GM) solve_one<T, GM>(*P, p0 + 3 * b, v0 + 3 * b, goal + 3 * b, hg, xw, x + (long)n * b, \
                              acc + 3L * N * b, att + 3L * N * b, rates + 3L * N * b, thrust + (long)N * b, st)
+#define CALL(T) do { if (P->gradient_mode == 1) CALL1(T, 1); else CALL1(T, 0); } while (0)
         if (N <= 8) CALL(8);
         else if (N <= 20) CALL(20);
         else CALL(32);
 #undef CALL
+#undef CALL1
         cost[b] = st.f; nit[b] = st.nit; nfev[b] = st.nfev; status[b] = st.status; task[b] = st.task;
     }
     return 0;

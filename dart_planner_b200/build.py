@@ -20,7 +20,7 @@ UNITS = {
     "mapper_kernels.cu": ["-fmad=false"],
     "probe_kernels.cu": [],
 }
-HEADERS = [os.path.join(CSRC, "se3mpc_core.cuh"),
+HEADERS = [os.path.join(CSRC, "se3mpc_core.cuh"), os.path.join(CSRC, "map_query.cuh"),
            os.path.join(HERE, "..", "include", "dart_se3mpc.h")]
 
 

@@ -15,24 +15,13 @@
 #include <stdint.h>
 
 #include "../../include/dart_se3mpc.h"
+#include "map_query.cuh"
+
+using namespace dartb200;
 
 extern "C" void dart_count_launch_(void);
 
 namespace {
-
-__device__ __forceinline__ int vox(double p, double res) { return (int)floor(p / res); }
-
-__device__ __forceinline__ double grid_at(const dart_grid &g, int kx, int ky, int kz)
-{
-    const int ix = kx - g.ox, iy = ky - g.oy, iz = kz - g.oz;
-    if (ix < 0 || iy < 0 || iz < 0 || ix >= g.nx || iy >= g.ny || iz >= g.nz) return g.prior;
-    return (double)__ldg(g.occ + ((long long)iz * g.ny + iy) * g.nx + ix);
-}
-
-__device__ __forceinline__ double query(const dart_grid &g, double x, double y, double z)
-{
-    return grid_at(g, vox(x, g.resolution), vox(y, g.resolution), vox(z, g.resolution));
-}
 
 __global__ void __launch_bounds__(256)
 map_query_kernel(const __grid_constant__ dart_grid g, long long B, long long ld, const double *pos,
@@ -55,15 +44,7 @@ map_traj_safe_kernel(const __grid_constant__ dart_grid g, long long B, long long
             const double c[3] = {__ldg(pos + (long long)(3 * i) * ld + b),
                                  __ldg(pos + (long long)(3 * i + 1) * ld + b),
                                  __ldg(pos + (long long)(3 * i + 2) * ld + b)};
-            bool col = query(g, c[0], c[1], c[2]) > thr;
-#pragma unroll
-            for (int axis = 0; axis < 3; ++axis)
-#pragma unroll
-                for (int dir = -1; dir <= 1; dir += 2) {
-                    double q[3] = {c[0], c[1], c[2]};
-                    q[axis] = c[axis] + (double)dir * margin;
-                    col = col || (query(g, q[0], q[1], q[2]) > thr);
-                }
+            const bool col = position_collides(g, c[0], c[1], c[2], margin, thr);
             if (col) hit = i;
         }
         first_hit[b] = hit;

@@ -14,6 +14,7 @@
 #include <atomic>
 #include <mutex>
 
+#include "map_query.cuh"
 #include "se3mpc_core.cuh"
 
 using namespace dartb200;
@@ -32,6 +33,11 @@ struct SolveArgs {
     double *x_out, *cost;
     int *nit, *nfev, *status, *task;
     double *acc, *att, *rates, *thrust;
+    /* fused post-solve safety check (is_trajectory_safe on the solved positions); off when
+     * first_hit == nullptr */
+    dart_grid grid;
+    double margin, threshold;
+    int *first_hit;
 };
 
 template <int LANES, int TPL, int BLOCK, int MINB, int GM>
@@ -102,6 +108,18 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
                 }
                 if (a.thrust) a.thrust[(long long)k * ld + b] = th;
             });
+        }
+        if (A.first_hit) {
+            /* each lane tests its own timesteps against the map; the first colliding index is
+             * the minimum over the group (explicit_geometric_mapper.py:195-219) */
+            int hit = 0x7fffffff;
+#pragma unroll
+            for (int tt = TPL - 1; tt >= 0; --tt)
+                if (sv.act[tt] && position_collides(A.grid, sv.x[tt * 9], sv.x[tt * 9 + 1], sv.x[tt * 9 + 2],
+                                                    A.margin, A.threshold))
+                    hit = sv.grp.lane() * TPL + tt;
+            hit = sv.grp.mini(hit);
+            if (sv.grp.leader()) A.first_hit[b] = (hit == 0x7fffffff) ? -1 : hit;
         }
         (void)N;
     }
@@ -272,6 +290,49 @@ int dart_se3mpc_kernel_info(const dart_se3mpc_params *params, int64_t B, int32_t
     return DART_OK;
 }
 
+int dart_se3mpc_solve_batch_map(const dart_se3mpc_params *params, int64_t B, int64_t ld,
+                                const double *p0, const double *v0, const double *goal,
+                                const uint8_t *has_goal, const double *x_warm,
+                                const uint8_t *warm_mask, double *x_out, double *cost, int32_t *nit,
+                                int32_t *nfev, int32_t *status, int32_t *task, double *acc,
+                                double *att, double *rates, double *thrust, const dart_grid *grid,
+                                double margin, double threshold, int32_t *first_hit,
+                                void *cuda_stream)
+{
+    int rc = check_params(params);
+    if (rc) return rc;
+    if (B < 0 || ld < B || !p0 || !v0 || !goal) return DART_E_BADARG;
+    if (first_hit && (!grid || !grid->occ || grid->nx <= 0 || grid->ny <= 0 || grid->nz <= 0 ||
+                      !(grid->resolution > 0.0)))
+        return DART_E_BADARG;
+    if (B == 0) return DART_OK;
+    KernelChoice *k = pick_kernel(params->horizon);
+    rc = prepare(k);
+    if (rc) return rc;
+    SolveArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = B; a.ld = ld;
+    a.p0 = p0; a.v0 = v0; a.goal = goal; a.has_goal = has_goal;
+    a.x_warm = x_warm; a.warm_mask = warm_mask;
+    a.x_out = x_out; a.cost = cost; a.nit = nit; a.nfev = nfev; a.status = status; a.task = task;
+    a.acc = acc; a.att = att; a.rates = rates; a.thrust = thrust;
+    if (first_hit) {
+        a.grid = *grid;
+        a.margin = margin;
+        a.threshold = threshold;
+        a.first_hit = first_hit;
+    }
+    dart_se3mpc_params P = *params;
+    void *args[] = {(void *)&P, (void *)&a};
+    const long long grid_blocks = grid_for(*k, B);
+    const void *fn = params->gradient_mode == 1 ? k->fn_exact : k->fn;
+    cudaError_t e = cudaLaunchKernel(fn, dim3((unsigned)grid_blocks), dim3(k->block), args,
+                                     smem_bytes(*k), (cudaStream_t)cuda_stream);
+    if (e != cudaSuccess) return set_err(e, "cudaLaunchKernel(se3mpc_solve)");
+    g_launches.fetch_add(1);
+    return DART_OK;
+}
+
 int dart_se3mpc_solve_batch(const dart_se3mpc_params *params, int64_t B, int64_t ld,
                             const double *p0, const double *v0, const double *goal,
                             const uint8_t *has_goal, const double *x_warm,
@@ -279,28 +340,9 @@ int dart_se3mpc_solve_batch(const dart_se3mpc_params *params, int64_t B, int64_t
                             int32_t *nfev, int32_t *status, int32_t *task, double *acc,
                             double *att, double *rates, double *thrust, void *cuda_stream)
 {
-    int rc = check_params(params);
-    if (rc) return rc;
-    if (B < 0 || ld < B || !p0 || !v0 || !goal) return DART_E_BADARG;
-    if (B == 0) return DART_OK;
-    KernelChoice *k = pick_kernel(params->horizon);
-    rc = prepare(k);
-    if (rc) return rc;
-    SolveArgs a;
-    a.B = B; a.ld = ld;
-    a.p0 = p0; a.v0 = v0; a.goal = goal; a.has_goal = has_goal;
-    a.x_warm = x_warm; a.warm_mask = warm_mask;
-    a.x_out = x_out; a.cost = cost; a.nit = nit; a.nfev = nfev; a.status = status; a.task = task;
-    a.acc = acc; a.att = att; a.rates = rates; a.thrust = thrust;
-    dart_se3mpc_params P = *params;
-    void *args[] = {(void *)&P, (void *)&a};
-    const long long grid = grid_for(*k, B);
-    const void *fn = params->gradient_mode == 1 ? k->fn_exact : k->fn;
-    cudaError_t e = cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(k->block), args,
-                                     smem_bytes(*k), (cudaStream_t)cuda_stream);
-    if (e != cudaSuccess) return set_err(e, "cudaLaunchKernel(se3mpc_solve)");
-    g_launches.fetch_add(1);
-    return DART_OK;
+    return dart_se3mpc_solve_batch_map(params, B, ld, p0, v0, goal, has_goal, x_warm, warm_mask, x_out,
+                                       cost, nit, nfev, status, task, acc, att, rates, thrust, nullptr,
+                                       0.0, 0.0, nullptr, cuda_stream);
 }
 
 /* ---- host-buffer entry: staged through a cached per-thread device workspace --------------- */

@@ -53,6 +53,7 @@ class BatchSolution:
     B: int
     out: Any     # (19N+1, ld) float64
     meta: Any    # (4, ld) int32 rows: nit, nfev, status, task
+    hit: Any = None   # (ld,) int32 first colliding position index (-1 safe) when a map was given
 
     def _rows(self, lo, hi):
         return self.out[lo:hi, : self.B]
@@ -116,11 +117,25 @@ class BatchSolution:
     def success(self):
         return self.status == 0
 
+    @property
+    def first_hit(self):
+        """is_trajectory_safe's collision index per problem (-1 = safe); needs `grid=`."""
+        if self.hit is None:
+            raise ValueError("no occupancy grid was passed to the solve")
+        return self.hit[: self.B]
+
+    @property
+    def safe(self):
+        return self.first_hit < 0
+
     def numpy(self) -> "HostSolution":
         """Copy everything to host ndarrays with the reference's shapes."""
         out = self.out[:, : self.B].cpu().numpy()
         meta = self.meta[:, : self.B].cpu().numpy()
-        return HostSolution.from_blocks(self.N, out, meta)
+        hs = HostSolution.from_blocks(self.N, out, meta)
+        if self.hit is not None:
+            hs.first_hit = self.hit[: self.B].cpu().numpy()
+        return hs
 
 
 @dataclass
@@ -135,6 +150,7 @@ class HostSolution:
     attitudes: np.ndarray
     body_rates: np.ndarray
     thrusts: np.ndarray
+    first_hit: Optional[np.ndarray] = None
 
     @staticmethod
     def from_blocks(N: int, out: np.ndarray, meta: np.ndarray) -> "HostSolution":
@@ -171,13 +187,17 @@ class HostSolution:
 
 def solve_batch_tensors(params: _cabi.Params, inp, B: int, *, has_goal=None, x_warm=None,
                         warm_mask=None, out=None, meta=None, stream=None,
-                        outputs: str = "all") -> BatchSolution:
+                        outputs: str = "all", grid=None, safety_margin: float = 1.0,
+                        collision_threshold: float = 0.6, hit=None) -> BatchSolution:
     """Lowest Python level: device tensors in, device tensors out, one kernel launch.
 
     inp      : (9, ld) float64 CUDA tensor, rows [p0 xyz | v0 xyz | goal xyz]
     has_goal : (ld,) uint8 or None;  x_warm : (9N, ld) float64 or None;  warm_mask (ld,) uint8
     out/meta : optional preallocated (19N+1, ld) float64 / (4, ld) int32
     outputs  : "all" | "controls" (x, cost, counters only; no derived rows are written)
+    grid     : DenseOccupancyGrid or None; when given, the kernel also runs the reference's
+               post-hoc `is_trajectory_safe(positions, safety_margin, collision_threshold)` on
+               every solved trajectory (fused, same launch) -> BatchSolution.first_hit
     """
     torch = _torch()
     L = _cabi.lib()
@@ -200,8 +220,14 @@ def solve_batch_tensors(params: _cabi.Params, inp, B: int, *, has_goal=None, x_w
         stream = torch.cuda.current_stream(inp.device)
     base, es = out.data_ptr(), 8 * ld
     derived = outputs == "all"
+    g = None
+    if grid is not None:
+        g = grid._grid()
+        if hit is None:
+            hit = torch.empty(ld, dtype=torch.int32, device=inp.device)
+        assert hit.is_cuda and hit.dtype == torch.int32 and hit.shape == (ld,) and hit.is_contiguous()
     with torch.cuda.device(inp.device):
-        rc = L.dart_se3mpc_solve_batch(
+        rc = L.dart_se3mpc_solve_batch_map(
             C.byref(params), B, ld, inp.data_ptr(), inp.data_ptr() + 3 * es, inp.data_ptr() + 6 * es,
             _ptr(has_goal), _ptr(x_warm), _ptr(warm_mask),
             base, base + 9 * N * es,
@@ -210,9 +236,11 @@ def solve_batch_tensors(params: _cabi.Params, inp, B: int, *, has_goal=None, x_w
             base + (12 * N + 1) * es if derived else None,
             base + (15 * N + 1) * es if derived else None,
             base + (18 * N + 1) * es if derived else None,
+            C.byref(g) if g is not None else None, float(safety_margin), float(collision_threshold),
+            hit.data_ptr() if g is not None else None,
             stream.cuda_stream)
-    _cabi.check(rc, "dart_se3mpc_solve_batch")
-    return BatchSolution(N=N, B=B, out=out, meta=meta)
+    _cabi.check(rc, "dart_se3mpc_solve_batch_map")
+    return BatchSolution(N=N, B=B, out=out, meta=meta, hit=hit if g is not None else None)
 
 
 class BatchWorkspace:
@@ -237,6 +265,7 @@ class BatchWorkspace:
         self.has_goal = None
         self.x_warm = None
         self.warm_mask = None
+        self.grid, self.safety_margin, self.collision_threshold, self.hit = None, 1.0, 0.6, None
         self.h_inp = self.h_out = self.h_meta = None
         if pinned:
             self.h_inp = torch.zeros((9, self.ld), dtype=torch.float64).pin_memory()
@@ -291,10 +320,18 @@ class BatchWorkspace:
         self.has_goal = torch.ones(self.ld, dtype=torch.uint8, device=self.device)
         self.has_goal[: self.B] = h
 
+    def set_map(self, grid, safety_margin: float = 1.0, collision_threshold: float = 0.6):
+        """Attach a DenseOccupancyGrid: every solve also runs the fused trajectory safety check."""
+        torch = _torch()
+        self.grid, self.safety_margin, self.collision_threshold = grid, safety_margin, collision_threshold
+        self.hit = None if grid is None else torch.full((self.ld,), -1, dtype=torch.int32, device=self.device)
+
     def solve_device(self, stream=None) -> BatchSolution:
         return solve_batch_tensors(self.params, self.inp, self.B, has_goal=self.has_goal,
                                    x_warm=self.x_warm, warm_mask=self.warm_mask, out=self.out,
-                                   meta=self.meta, stream=stream, outputs=self.outputs)
+                                   meta=self.meta, stream=stream, outputs=self.outputs,
+                                   grid=self.grid, safety_margin=self.safety_margin,
+                                   collision_threshold=self.collision_threshold, hit=self.hit)
 
     def stage_host_inputs(self, p0, v0, goal):
         """Write (B,3) host arrays into the pinned SoA staging block (host-side transpose)."""
@@ -325,7 +362,8 @@ class BatchWorkspace:
 def plan_batch(positions, velocities, goals, config: Optional[SE3MPCConfig] = None, *,
                mass: float = 1.5, gravity: float = 9.81, dt: Optional[float] = None,
                has_goal=None, x_warm=None, warm_mask=None, gradient_mode: int = 0,
-               device=None, outputs: str = "all", to_host: bool = False):
+               device=None, outputs: str = "all", to_host: bool = False, grid=None,
+               safety_margin: float = 1.0, collision_threshold: float = 0.6):
     """Solve B independent SE(3)-MPC problems in one call.
 
     positions, velocities, goals : (B, 3) array-likes (NumPy or torch, host or device)
@@ -333,6 +371,8 @@ def plan_batch(positions, velocities, goals, config: Optional[SE3MPCConfig] = No
              exposes dt explicitly; only the drop-in class applies the reference's 1/400 s
              override)
     x_warm : (B, 9N) previous solutions for warm starts (se3_mpc_planner.py:294-327)
+    grid   : DenseOccupancyGrid; adds the fused post-hoc `is_trajectory_safe` check of every
+             solved trajectory (result.first_hit / result.safe)
     Returns a BatchSolution (device) or HostSolution (``to_host=True``).
     """
     cfg = config or SE3MPCConfig()
@@ -342,6 +382,8 @@ def plan_batch(positions, velocities, goals, config: Optional[SE3MPCConfig] = No
     ws.set_inputs_device(positions, velocities, goals)
     ws.set_has_goal(has_goal)
     ws.set_warm(x_warm, warm_mask)
+    if grid is not None:
+        ws.set_map(grid, safety_margin, collision_threshold)
     sol = ws.solve_device()
     return sol.numpy() if to_host else sol
 

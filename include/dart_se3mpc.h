@@ -63,6 +63,17 @@ typedef struct dart_se3mpc_params {
     double ftol;               /* 10*convergence_tolerance (:265)                          */
 } dart_se3mpc_params;
 
+/* ---- occupancy grid (perception/explicit_geometric_mapper.py) on a dense device grid ----
+ * occ: float32 [nz][ny][nx] (x fastest); voxel key (kx,ky,kz) = floor(p/res) lives at index
+ * (kx-ox, ky-oy, kz-oz); keys outside the grid read `prior` (the reference's dict miss, :168). */
+typedef struct dart_grid {
+    int32_t nx, ny, nz;
+    int32_t ox, oy, oz;
+    double resolution;
+    double prior;
+    const float *occ;
+} dart_grid;
+
 int dart_abi_version(void);
 const char *dart_last_cuda_error(void);
 
@@ -92,6 +103,20 @@ int dart_se3mpc_solve_batch(const dart_se3mpc_params *params, int64_t B, int64_t
                             int32_t *nfev, int32_t *status, int32_t *task, double *acc,
                             double *att, double *rates, double *thrust, void *cuda_stream);
 
+/* Solve + fused post-hoc safety check: the same solve, then `is_trajectory_safe`
+ * (explicit_geometric_mapper.py:195-219; as the callers use it after planning,
+ * cloud/main_improved_se3.py:128-130) on the N solved positions of every problem, inside the
+ * solve kernel (positions never leave registers).  first_hit [ld] int32: index of the first
+ * colliding position, -1 = safe.  grid/first_hit may be NULL (plain solve). */
+int dart_se3mpc_solve_batch_map(const dart_se3mpc_params *params, int64_t B, int64_t ld,
+                                const double *p0, const double *v0, const double *goal,
+                                const uint8_t *has_goal, const double *x_warm,
+                                const uint8_t *warm_mask, double *x_out, double *cost, int32_t *nit,
+                                int32_t *nfev, int32_t *status, int32_t *task, double *acc,
+                                double *att, double *rates, double *thrust, const dart_grid *grid,
+                                double margin, double threshold, int32_t *first_hit,
+                                void *cuda_stream);
+
 /* Same call with every buffer in HOST memory (pageable or pinned): stages through an
  * internal per-thread device workspace, copies in, solves, copies back and synchronises.
  * This is the plugin-level entry the drop-in planner's single-problem `plan()` uses. */
@@ -115,17 +140,6 @@ int dart_se3mpc_kernel_info(const dart_se3mpc_params *params, int64_t B, int32_t
  * 148*8 blocks x 256 threads, each running 8 independent DFMA chains of `iters` steps;
  * flops = threads * 8 * iters * 2.  `scratch`: >= 8 bytes of device memory. */
 int dart_fp64_probe(int32_t iters, int32_t *threads_out, double *scratch, void *cuda_stream);
-
-/* ---- occupancy grid (perception/explicit_geometric_mapper.py) on a dense device grid ----
- * occ: float32 [nz][ny][nx] (x fastest); voxel key (kx,ky,kz) = floor(p/res) lives at index
- * (kx-ox, ky-oy, kz-oz); keys outside the grid read `prior` (the reference's dict miss, :168). */
-typedef struct dart_grid {
-    int32_t nx, ny, nz;
-    int32_t ox, oy, oz;
-    double resolution;
-    double prior;
-    const float *occ;
-} dart_grid;
 
 /* query_occupancy_batch (:171-182): pos [3][ld] -> occ_out [ld] (float64 like the reference) */
 int dart_map_query_batch(const dart_grid *g, int64_t B, int64_t ld, const double *pos,

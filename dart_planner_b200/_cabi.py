@@ -50,7 +50,8 @@ class Grid(C.Structure):
 
 EXPORTS = [
     "dart_abi_version", "dart_last_cuda_error", "dart_se3mpc_default_params",
-    "dart_se3mpc_solve_batch", "dart_se3mpc_solve_batch_map", "dart_se3mpc_solve_batch_host",
+    "dart_se3mpc_solve_batch", "dart_se3mpc_solve_batch_map", "dart_se3mpc_closed_loop_step",
+    "dart_se3mpc_solve_batch_host",
     "dart_launch_count",
     "dart_se3mpc_kernel_info", "dart_map_query_batch", "dart_map_traj_safe_batch",
     "dart_map_trace_ray_batch", "dart_map_add_spheres", "dart_fp64_probe",
@@ -83,6 +84,9 @@ def lib():
     L.dart_se3mpc_solve_batch_map.argtypes = ([C.POINTER(Params), i64, i64] + [vp] * 16 +
                                               [C.POINTER(Grid), C.c_double, C.c_double, vp, vp])
     L.dart_se3mpc_solve_batch_map.restype = C.c_int
+    L.dart_se3mpc_closed_loop_step.argtypes = ([C.POINTER(Params), i64, i64] + [vp] * 5 + [i32] +
+                                               [vp] * 4 + [C.c_double, vp])
+    L.dart_se3mpc_closed_loop_step.restype = C.c_int
     L.dart_se3mpc_solve_batch_host.argtypes = [C.POINTER(Params), i64] + [vp] * 14
     L.dart_se3mpc_solve_batch_host.restype = C.c_int
     L.dart_launch_count.restype = C.c_int64

@@ -38,6 +38,10 @@ struct SolveArgs {
     dart_grid grid;
     double margin, threshold;
     int *first_hit;
+    /* fused plant step of the closed-loop simulation (off when p_next == nullptr): the state is
+     * advanced with the first control of the new solution; may alias p0 / v0 */
+    double *p_next, *v_next;
+    double plant_dt;
 };
 
 template <int LANES, int TPL, int BLOCK, int MINB, int GM>
@@ -63,9 +67,10 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
         sv.has_goal = A.has_goal ? (A.has_goal[b] != 0) : true;
         const bool warm = A.x_warm != nullptr && (A.warm_mask == nullptr || A.warm_mask[b] != 0);
         if (warm) {
+            /* plain loads: in the closed loop x_out aliases x_warm */
             const double *xw = A.x_warm + b;
             const long long ld = A.ld;
-            sv.warm_start(p0, v0, [xw, ld](int row) { return __ldg(xw + (long long)row * ld); });
+            sv.warm_start(p0, v0, [xw, ld](int row) { return xw[(long long)row * ld]; });
         } else
             sv.cold_start(p0, v0);
         SolveStats st;
@@ -120,6 +125,18 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
                     hit = sv.grp.lane() * TPL + tt;
             hit = sv.grp.mini(hit);
             if (sv.grp.leader()) A.first_hit[b] = (hit == 0x7fffffff) ? -1 : hit;
+        }
+        if (A.p_next && sv.grp.leader()) {
+            /* reference planner model (se3_mpc_planner.py:430-431, :445-459) driven by T_0:
+             * a = T_0/m - g e3;  p <- p + v dt + (0.5 a) dt^2;  v <- v + a dt.  Every operation
+             * individually rounded (NumPy's order). */
+            const double dt = A.plant_dt, dt2 = DP_MUL(dt, dt);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const double a = DP_ADD(ddiv(sv.x[6 + c], P.mass), c == 2 ? -P.gravity : -0.0);
+                A.p_next[c * A.ld + b] = DP_ADD(DP_ADD(p0[c], DP_MUL(v0[c], dt)), DP_MUL(DP_MUL(0.5, a), dt2));
+                A.v_next[c * A.ld + b] = DP_ADD(v0[c], DP_MUL(a, dt));
+            }
         }
         (void)N;
     }
@@ -290,6 +307,23 @@ int dart_se3mpc_kernel_info(const dart_se3mpc_params *params, int64_t B, int32_t
     return DART_OK;
 }
 
+static int launch_solve(const dart_se3mpc_params *params, const SolveArgs &a, void *cuda_stream)
+{
+    KernelChoice *k = pick_kernel(params->horizon);
+    int rc = prepare(k);
+    if (rc) return rc;
+    dart_se3mpc_params P = *params;
+    SolveArgs args_copy = a;
+    void *args[] = {(void *)&P, (void *)&args_copy};
+    const long long grid_blocks = grid_for(*k, a.B);
+    const void *fn = params->gradient_mode == 1 ? k->fn_exact : k->fn;
+    cudaError_t e = cudaLaunchKernel(fn, dim3((unsigned)grid_blocks), dim3(k->block), args,
+                                     smem_bytes(*k), (cudaStream_t)cuda_stream);
+    if (e != cudaSuccess) return set_err(e, "cudaLaunchKernel(se3mpc_solve)");
+    g_launches.fetch_add(1);
+    return DART_OK;
+}
+
 int dart_se3mpc_solve_batch_map(const dart_se3mpc_params *params, int64_t B, int64_t ld,
                                 const double *p0, const double *v0, const double *goal,
                                 const uint8_t *has_goal, const double *x_warm,
@@ -306,9 +340,6 @@ int dart_se3mpc_solve_batch_map(const dart_se3mpc_params *params, int64_t B, int
                       !(grid->resolution > 0.0)))
         return DART_E_BADARG;
     if (B == 0) return DART_OK;
-    KernelChoice *k = pick_kernel(params->horizon);
-    rc = prepare(k);
-    if (rc) return rc;
     SolveArgs a;
     memset(&a, 0, sizeof(a));
     a.B = B; a.ld = ld;
@@ -322,15 +353,26 @@ int dart_se3mpc_solve_batch_map(const dart_se3mpc_params *params, int64_t B, int
         a.threshold = threshold;
         a.first_hit = first_hit;
     }
-    dart_se3mpc_params P = *params;
-    void *args[] = {(void *)&P, (void *)&a};
-    const long long grid_blocks = grid_for(*k, B);
-    const void *fn = params->gradient_mode == 1 ? k->fn_exact : k->fn;
-    cudaError_t e = cudaLaunchKernel(fn, dim3((unsigned)grid_blocks), dim3(k->block), args,
-                                     smem_bytes(*k), (cudaStream_t)cuda_stream);
-    if (e != cudaSuccess) return set_err(e, "cudaLaunchKernel(se3mpc_solve)");
-    g_launches.fetch_add(1);
-    return DART_OK;
+    return launch_solve(params, a, cuda_stream);
+}
+
+int dart_se3mpc_closed_loop_step(const dart_se3mpc_params *params, int64_t B, int64_t ld, double *p,
+                                 double *v, const double *goal, const uint8_t *has_goal, double *x,
+                                 int32_t warm, double *cost, int32_t *nit, int32_t *nfev,
+                                 int32_t *status, double plant_dt, void *cuda_stream)
+{
+    int rc = check_params(params);
+    if (rc) return rc;
+    if (B < 0 || ld < B || !p || !v || !goal || !x || !(plant_dt > 0.0)) return DART_E_BADARG;
+    if (B == 0) return DART_OK;
+    SolveArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = B; a.ld = ld;
+    a.p0 = p; a.v0 = v; a.goal = goal; a.has_goal = has_goal;
+    a.x_warm = warm ? x : nullptr;
+    a.x_out = x; a.cost = cost; a.nit = nit; a.nfev = nfev; a.status = status;
+    a.p_next = p; a.v_next = v; a.plant_dt = plant_dt;
+    return launch_solve(params, a, cuda_stream);
 }
 
 int dart_se3mpc_solve_batch(const dart_se3mpc_params *params, int64_t B, int64_t ld,

@@ -117,6 +117,18 @@ int dart_se3mpc_solve_batch_map(const dart_se3mpc_params *params, int64_t B, int
                                 double margin, double threshold, int32_t *first_hit,
                                 void *cuda_stream);
 
+/* One replanning step of the closed-loop receding-horizon simulation (BASELINE configs[4]),
+ * one launch: solve every problem from its resident state (p, v) -- cold start when warm == 0,
+ * else the warm start of se3_mpc_planner.py:294-327 from the previous solution held in x --
+ * write the new solution to x, then advance the state in place with the planner's own model
+ * (:430-431, :445-459) driven by the first control:  a = T_0/m - g e3,
+ * p <- p + v*dt + 0.5*a*dt^2,  v <- v + a*dt  (dt = plant_dt).
+ * p, v : [3][ld] in/out;  x : [9N][ld] in/out;  cost/nit/nfev/status may be NULL. */
+int dart_se3mpc_closed_loop_step(const dart_se3mpc_params *params, int64_t B, int64_t ld, double *p,
+                                 double *v, const double *goal, const uint8_t *has_goal, double *x,
+                                 int32_t warm, double *cost, int32_t *nit, int32_t *nfev,
+                                 int32_t *status, double plant_dt, void *cuda_stream);
+
 /* Same call with every buffer in HOST memory (pageable or pinned): stages through an
  * internal per-thread device workspace, copies in, solves, copies back and synchronises.
  * This is the plugin-level entry the drop-in planner's single-problem `plan()` uses. */

@@ -55,7 +55,15 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
     const int N = P.horizon;
     const long long stride = (long long)gridDim.x * GPB;
     double ws[MMAX][9 * TPL], wy[MMAX][9 * TPL]; /* per-lane S / Y pairs (local memory, L1) */
-    for (long long b = (long long)blockIdx.x * GPB + gib; b < A.B; b += stride) {
+    /* block-uniform trip count + a warp barrier per round: the sub-warps of a warp start every
+     * problem together (a sub-warp that converged early waits instead of running ahead into
+     * different code) */
+    (void)stride;
+    const long long rounds = (A.B + GPB - 1) / GPB;
+    for (long long blk = blockIdx.x; blk < rounds; blk += gridDim.x) {
+        __syncwarp();
+        const long long b = blk * GPB + gib;
+        if (b >= A.B) continue;
         Solver<SubWarp<LANES>, TPL, GM> sv(P, sm, ws, wy);
         double p0[3], v0[3];
 #pragma unroll

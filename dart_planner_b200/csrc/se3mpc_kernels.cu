@@ -400,9 +400,39 @@ namespace {
 struct HostWs {
     void *dev = nullptr;
     size_t cap = 0;
+    void *pin = nullptr; /* pinned host mirror of the workspace (small batches) */
+    size_t pin_cap = 0;
     cudaStream_t stream = nullptr;
 };
 thread_local HostWs g_ws;
+
+/* workspace layout for row pitch Bp (elements): fp64 rows [p0 3 | v0 3 | goal 3 | x_warm 9N |
+ * x 9N | cost 1 | acc 3N | att 3N | rates 3N | thrust N], int32 rows [nit nfev status task],
+ * u8 row [has_goal].  Inputs are one contiguous range, outputs another. */
+struct WsLayout {
+    size_t Bp, in_rows, out_off_rows, out_rows, int_off, hg_off, bytes;
+    WsLayout(int N, size_t Bp_) : Bp(Bp_)
+    {
+        in_rows = 9 + 9 * (size_t)N;
+        out_off_rows = in_rows;
+        out_rows = 9 * (size_t)N + 1 + 9 * (size_t)N + (size_t)N;
+        int_off = (in_rows + out_rows) * Bp * 8;
+        hg_off = int_off + 4 * Bp * 4;
+        bytes = hg_off + ((Bp + 7) / 8) * 8;
+    }
+};
+
+void rows_in(void *dst, size_t pitch, const void *src, size_t B, size_t rows, size_t esz)
+{
+    for (size_t r = 0; r < rows; ++r)
+        memcpy((char *)dst + r * pitch * esz, (const char *)src + r * B * esz, B * esz);
+}
+void rows_out(void *dst, const void *src, size_t pitch, size_t B, size_t rows, size_t esz)
+{
+    if (!dst) return;
+    for (size_t r = 0; r < rows; ++r)
+        memcpy((char *)dst + r * B * esz, (const char *)src + r * pitch * esz, B * esz);
+}
 }
 
 int dart_se3mpc_solve_batch_host(const dart_se3mpc_params *params, int64_t B,
@@ -415,40 +445,104 @@ int dart_se3mpc_solve_batch_host(const dart_se3mpc_params *params, int64_t B,
     if (rc) return rc;
     if (B < 0 || !p0 || !v0 || !goal) return DART_E_BADARG;
     if (B == 0) return DART_OK;
-    const int N = params->horizon;
-    const size_t Bp = (size_t)((B + 31) / 32 * 32); /* padded row pitch */
-    /* rows of 8-byte elements: p0 3, v0 3, goal 3, x_warm 9N, x 9N, cost 1, acc/att/rates 3N each,
-     * thrust N; then int32 rows nit, nfev, status, task; then u8 has_goal */
-    const size_t drows = 9 + 9 * (size_t)N + 9 * (size_t)N + 1 + 9 * (size_t)N + (size_t)N;
-    const size_t bytes = drows * Bp * 8 + 4 * Bp * 4 + Bp;
+    const size_t N = (size_t)params->horizon;
+    /* small batches (the drop-in planner's single solve): ONE pinned H2D copy, one launch, ONE
+     * D2H copy; large batches copy rows straight from / to the caller's buffers */
+    const bool staged = B <= 512;
+    const size_t Bp = staged ? (size_t)((B + 3) / 4 * 4) : (size_t)((B + 31) / 32 * 32);
+    const WsLayout L((int)N, Bp);
     cudaError_t e;
     if (!g_ws.stream) {
         e = cudaStreamCreateWithFlags(&g_ws.stream, cudaStreamNonBlocking);
         if (e != cudaSuccess) return set_err(e, "cudaStreamCreate");
     }
-    if (g_ws.cap < bytes) {
+    if (g_ws.cap < L.bytes) {
         if (g_ws.dev) cudaFree(g_ws.dev);
         g_ws.dev = nullptr;
         g_ws.cap = 0;
-        e = cudaMalloc(&g_ws.dev, bytes);
+        e = cudaMalloc(&g_ws.dev, L.bytes);
         if (e != cudaSuccess) return set_err(e, "cudaMalloc(workspace)");
-        g_ws.cap = bytes;
+        g_ws.cap = L.bytes;
+    }
+    if (staged && g_ws.pin_cap < L.bytes) {
+        if (g_ws.pin) cudaFreeHost(g_ws.pin);
+        g_ws.pin = nullptr;
+        g_ws.pin_cap = 0;
+        e = cudaHostAlloc(&g_ws.pin, L.bytes, cudaHostAllocDefault);
+        if (e != cudaSuccess) return set_err(e, "cudaHostAlloc(staging)");
+        g_ws.pin_cap = L.bytes;
     }
     cudaStream_t s = g_ws.stream;
-    double *d = (double *)g_ws.dev;
+    char *base = (char *)g_ws.dev;
+    double *d = (double *)base;
     double *d_p0 = d, *d_v0 = d_p0 + 3 * Bp, *d_goal = d_v0 + 3 * Bp, *d_xw = d_goal + 3 * Bp;
-    double *d_x = d_xw + 9 * (size_t)N * Bp, *d_cost = d_x + 9 * (size_t)N * Bp;
-    double *d_acc = d_cost + Bp, *d_att = d_acc + 3 * (size_t)N * Bp, *d_rates = d_att + 3 * (size_t)N * Bp;
-    double *d_thr = d_rates + 3 * (size_t)N * Bp;
-    int32_t *d_nit = (int32_t *)(d_thr + (size_t)N * Bp), *d_nfev = d_nit + Bp, *d_status = d_nfev + Bp,
+    double *d_x = d_xw + 9 * N * Bp, *d_cost = d_x + 9 * N * Bp;
+    double *d_acc = d_cost + Bp, *d_att = d_acc + 3 * N * Bp, *d_rates = d_att + 3 * N * Bp;
+    double *d_thr = d_rates + 3 * N * Bp;
+    int32_t *d_nit = (int32_t *)(base + L.int_off), *d_nfev = d_nit + Bp, *d_status = d_nfev + Bp,
             *d_task = d_status + Bp;
-    uint8_t *d_hg = (uint8_t *)(d_task + Bp);
+    uint8_t *d_hg = (uint8_t *)(base + L.hg_off);
+    const size_t in_bytes = (x_warm ? L.in_rows : 9) * Bp * 8;
+    if (staged) {
+        char *h = (char *)g_ws.pin;
+        rows_in(h, Bp, p0, (size_t)B, 3, 8);
+        rows_in(h + 3 * Bp * 8, Bp, v0, (size_t)B, 3, 8);
+        rows_in(h + 6 * Bp * 8, Bp, goal, (size_t)B, 3, 8);
+        if (x_warm) rows_in(h + 9 * Bp * 8, Bp, x_warm, (size_t)B, 9 * N, 8);
+        e = cudaMemcpyAsync(base, h, in_bytes, cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) return set_err(e, "cudaMemcpyAsync H2D");
+        if (has_goal) {
+            memcpy(h + L.hg_off, has_goal, (size_t)B);
+            e = cudaMemcpyAsync(d_hg, h + L.hg_off, (size_t)B, cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) return set_err(e, "cudaMemcpyAsync H2D");
+        }
+    } else {
 #define H2D(dst, src, rows, esz)                                                              \
     do {                                                                                      \
         e = cudaMemcpy2DAsync(dst, Bp * (esz), src, (size_t)B * (esz), (size_t)B * (esz), rows, \
                               cudaMemcpyHostToDevice, s);                                     \
         if (e != cudaSuccess) return set_err(e, "cudaMemcpy2DAsync H2D");                     \
     } while (0)
+        H2D(d_p0, p0, 3, 8);
+        H2D(d_v0, v0, 3, 8);
+        H2D(d_goal, goal, 3, 8);
+        if (has_goal) H2D(d_hg, has_goal, 1, 1);
+        if (x_warm) H2D(d_xw, x_warm, 9 * N, 8);
+#undef H2D
+    }
+    /* the staged path always produces every output row (one copy back); the direct path only
+     * the rows the caller asked for */
+    const bool all = staged;
+    rc = dart_se3mpc_solve_batch(params, B, (int64_t)Bp, d_p0, d_v0, d_goal, has_goal ? d_hg : nullptr,
+                                 x_warm ? d_xw : nullptr, nullptr, (all || x_out) ? d_x : nullptr,
+                                 (all || cost) ? d_cost : nullptr, (all || nit) ? d_nit : nullptr,
+                                 (all || nfev) ? d_nfev : nullptr, (all || status) ? d_status : nullptr,
+                                 nullptr, (all || acc) ? d_acc : nullptr, (all || att) ? d_att : nullptr,
+                                 (all || rates) ? d_rates : nullptr, (all || thrust) ? d_thr : nullptr,
+                                 (void *)s);
+    if (rc) return rc;
+    if (staged) {
+        char *h = (char *)g_ws.pin;
+        const size_t out_off = L.out_off_rows * Bp * 8;
+        e = cudaMemcpyAsync(h + out_off, base + out_off, L.hg_off - out_off, cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) return set_err(e, "cudaMemcpyAsync D2H");
+        e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) return set_err(e, "cudaStreamSynchronize");
+        const double *hd = (const double *)h;
+        const double *h_x = hd + L.in_rows * Bp, *h_cost = h_x + 9 * N * Bp, *h_acc = h_cost + Bp,
+                     *h_att = h_acc + 3 * N * Bp, *h_rates = h_att + 3 * N * Bp, *h_thr = h_rates + 3 * N * Bp;
+        const int32_t *h_nit = (const int32_t *)(h + L.int_off);
+        rows_out(x_out, h_x, Bp, (size_t)B, 9 * N, 8);
+        rows_out(cost, h_cost, Bp, (size_t)B, 1, 8);
+        rows_out(acc, h_acc, Bp, (size_t)B, 3 * N, 8);
+        rows_out(att, h_att, Bp, (size_t)B, 3 * N, 8);
+        rows_out(rates, h_rates, Bp, (size_t)B, 3 * N, 8);
+        rows_out(thrust, h_thr, Bp, (size_t)B, N, 8);
+        rows_out(nit, h_nit, Bp, (size_t)B, 1, 4);
+        rows_out(nfev, h_nit + Bp, Bp, (size_t)B, 1, 4);
+        rows_out(status, h_nit + 2 * Bp, Bp, (size_t)B, 1, 4);
+        return DART_OK;
+    }
 #define D2H(dst, src, rows, esz)                                                              \
     do {                                                                                      \
         if (dst) {                                                                            \
@@ -457,28 +551,15 @@ int dart_se3mpc_solve_batch_host(const dart_se3mpc_params *params, int64_t B,
             if (e != cudaSuccess) return set_err(e, "cudaMemcpy2DAsync D2H");                 \
         }                                                                                     \
     } while (0)
-    H2D(d_p0, p0, 3, 8);
-    H2D(d_v0, v0, 3, 8);
-    H2D(d_goal, goal, 3, 8);
-    if (has_goal) H2D(d_hg, has_goal, 1, 1);
-    if (x_warm) H2D(d_xw, x_warm, 9 * (size_t)N, 8);
-    rc = dart_se3mpc_solve_batch(params, B, (int64_t)Bp, d_p0, d_v0, d_goal, has_goal ? d_hg : nullptr,
-                                 x_warm ? d_xw : nullptr, nullptr, x_out ? d_x : nullptr,
-                                 cost ? d_cost : nullptr, nit ? d_nit : nullptr,
-                                 nfev ? d_nfev : nullptr, status ? d_status : nullptr, nullptr,
-                                 acc ? d_acc : nullptr, att ? d_att : nullptr,
-                                 rates ? d_rates : nullptr, thrust ? d_thr : nullptr, (void *)s);
-    if (rc) return rc;
-    D2H(x_out, d_x, 9 * (size_t)N, 8);
+    D2H(x_out, d_x, 9 * N, 8);
     D2H(cost, d_cost, 1, 8);
     D2H(nit, d_nit, 1, 4);
     D2H(nfev, d_nfev, 1, 4);
     D2H(status, d_status, 1, 4);
-    D2H(acc, d_acc, 3 * (size_t)N, 8);
-    D2H(att, d_att, 3 * (size_t)N, 8);
-    D2H(rates, d_rates, 3 * (size_t)N, 8);
-    D2H(thrust, d_thr, (size_t)N, 8);
-#undef H2D
+    D2H(acc, d_acc, 3 * N, 8);
+    D2H(att, d_att, 3 * N, 8);
+    D2H(rates, d_rates, 3 * N, 8);
+    D2H(thrust, d_thr, N, 8);
 #undef D2H
     e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) return set_err(e, "cudaStreamSynchronize");

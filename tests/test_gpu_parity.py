@@ -198,3 +198,47 @@ def test_dropin_planner_api():
     em = p3.update_plan(state, [{"position": [1, 1, 1], "radius": 0.5}])
     assert em.positions.shape == (6, 3) and len(p3.obstacles) == 1
     assert dp.planner.PlannerFactory.create("se3_mpc").__class__ is dp.SE3MPCPlanner
+
+
+def test_host_buffer_entry_matches_device_entry():
+    """dart_se3mpc_solve_batch_host (host pointers in/out; staged single-copy path for B <= 512,
+    row copies above) returns exactly what the device-pointer entry computes."""
+    import ctypes as C
+    import dart_planner_b200 as dp
+    from dart_planner_b200 import _cabi
+    from dart_planner_b200.config import make_params
+    L = _cabi.lib()
+    N = 8
+    cfg = dp.SE3MPCConfig(prediction_horizon=N, dt=0.1)
+    params = make_params(cfg)
+    vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    for B in (1, 5, 512, 513, 2000):
+        p0, v0, goal = bench_inputs(40 + B, B, 1.0)
+        first = dp.plan_batch(p0, v0, goal, cfg, to_host=True)
+        hg = (np.arange(B) % 4 != 0).astype(np.uint8)
+        for warm, use_hg in ((None, None), (first.x, hg)):
+            ref = dp.plan_batch(p0, v0, goal, cfg, x_warm=warm, has_goal=use_hg, to_host=True)
+            soa = lambda a: np.ascontiguousarray(np.asarray(a, np.float64).reshape(B, -1).T)  # noqa: E731
+            i_p0, i_v0, i_goal = soa(p0), soa(v0), soa(goal)
+            i_xw = None if warm is None else soa(warm)
+            x = np.zeros((9 * N, B)); cost = np.zeros(B)
+            nit = np.zeros(B, np.int32); nfev = np.zeros(B, np.int32); status = np.zeros(B, np.int32)
+            acc = np.zeros((3 * N, B)); att = np.zeros((3 * N, B)); rates = np.zeros((3 * N, B))
+            thr = np.zeros((N, B))
+            rc = L.dart_se3mpc_solve_batch_host(C.byref(params), B, vp(i_p0), vp(i_v0), vp(i_goal),
+                                                vp(use_hg), vp(i_xw), vp(x), vp(cost), vp(nit), vp(nfev),
+                                                vp(status), vp(acc), vp(att), vp(rates), vp(thr))
+            assert rc == 0
+            np.testing.assert_array_equal(x.T, ref.x)
+            np.testing.assert_array_equal(cost, ref.cost)
+            np.testing.assert_array_equal(nit, ref.nit)
+            np.testing.assert_array_equal(nfev, ref.nfev)
+            np.testing.assert_array_equal(status, ref.status)
+            np.testing.assert_array_equal(acc.T.reshape(B, N, 3), ref.accelerations)
+            np.testing.assert_array_equal(att.T.reshape(B, N, 3), ref.attitudes)
+            np.testing.assert_array_equal(rates.T.reshape(B, N, 3), ref.body_rates)
+            np.testing.assert_array_equal(thr.T, ref.thrusts)
+        # outputs are optional
+        rc = L.dart_se3mpc_solve_batch_host(C.byref(params), B, vp(i_p0), vp(i_v0), vp(i_goal), None, None,
+                                            vp(x), None, None, None, None, None, None, None, None)
+        assert rc == 0

@@ -35,6 +35,7 @@ class Params(C.Structure):
         ("min_thrust", C.c_double), ("max_thrust", C.c_double),
         ("w_pos", C.c_double), ("w_vel", C.c_double), ("w_acc", C.c_double),
         ("w_thrust", C.c_double), ("gtol", C.c_double), ("ftol", C.c_double),
+        ("w_obstacle", C.c_double), ("obstacle_free_level", C.c_double),
     ]
 
 

@@ -91,7 +91,8 @@ class AttrDict(dict):
 
 def make_params(cfg: SE3MPCConfig, *, mass: float = 1.5, gravity: float = 9.81,
                 dt: Optional[float] = None, gradient_mode: int = 0, max_corrections: int = 10,
-                max_linesearch: int = 20, max_fun: int = 15000) -> Params:
+                max_linesearch: int = 20, max_fun: int = 15000,
+                obstacle_free_level: float = 0.5) -> Params:
     """SE3MPCConfig -> the C-ABI parameter block, exactly as the reference feeds SciPy
     (se3_mpc_planner.py:256-268, :378-402)."""
     p = Params()
@@ -116,6 +117,8 @@ def make_params(cfg: SE3MPCConfig, *, mass: float = 1.5, gravity: float = 9.81,
     p.w_thrust = float(cfg.thrust_weight)
     p.gtol = float(cfg.convergence_tolerance)
     p.ftol = float(cfg.convergence_tolerance * 10)
+    p.w_obstacle = float(cfg.obstacle_weight)          # only read in gradient_mode 2
+    p.obstacle_free_level = float(obstacle_free_level)
     return p
 
 

@@ -65,6 +65,11 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
         const long long b = blk * GPB + gib;
         if (b >= A.B) continue;
         Solver<SubWarp<LANES>, TPL, GM> sv(P, sm, ws, wy);
+        if (GM == 2) {
+            sv.obs.g = A.grid;
+            sv.obs.w = P.w_obstacle;
+            sv.obs.free_level = P.obstacle_free_level;
+        }
         double p0[3], v0[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -153,6 +158,7 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
 struct KernelChoice {
     const void *fn;       /* gradient_mode 0: the reference gradient (:552-580) */
     const void *fn_exact; /* gradient_mode 1: exact gradient of :516-550       */
+    const void *fn_grid;  /* gradient_mode 2: mode 0 + occupancy-grid penalty  */
     int lanes, tpl, block, minb;
     int occ_blocks; /* resident blocks per SM (queried once) */
     int regs;
@@ -167,6 +173,7 @@ KernelChoice make_choice()
     KernelChoice k;
     k.fn = (const void *)se3mpc_solve_kernel<LANES, TPL, BLK, MINB, 0>;
     k.fn_exact = (const void *)se3mpc_solve_kernel<LANES, TPL, BLK, MINB, 1>;
+    k.fn_grid = (const void *)se3mpc_solve_kernel<LANES, TPL, BLK, MINB, 2>;
     k.lanes = LANES;
     k.tpl = TPL;
     k.block = BLK;
@@ -181,8 +188,7 @@ KernelChoice g_kernels[] = {
     make_choice<4, 1, 2>(), make_choice<8, 1, 2>(), make_choice<16, 1, 2>(),
     make_choice<32, 1, 2>(), make_choice<32, 2, 2>(),
     /* tuning variants, selected with DART_SE3MPC_VARIANT=<index> (tools/kbench.py) */
-    make_choice<4, 2, 2>(), make_choice<8, 1, 3>(), make_choice<8, 1, 4>(), make_choice<8, 1, 4, 64>(),
-    make_choice<8, 1, 8, 64>(),
+    make_choice<8, 1, 3>(), make_choice<8, 1, 4, 64>(),
 };
 std::mutex g_mu;
 int g_sms = 0;
@@ -221,7 +227,7 @@ int prepare(KernelChoice *k)
         if (e != cudaSuccess) return set_err(e, "cudaDeviceGetAttribute");
     }
     const int smem = smem_bytes(*k);
-    for (const void *fn : {k->fn, k->fn_exact}) {
+    for (const void *fn : {k->fn, k->fn_exact, k->fn_grid}) {
         e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return set_err(e, "cudaFuncSetAttribute(smem)");
     }
@@ -229,7 +235,7 @@ int prepare(KernelChoice *k)
      * the driver reserves); the rest stays L1 for the per-lane S/Y pairs in local memory */
     int carve = (int)((long long)k->minb * (smem + 1024) * 100 / (228 * 1024)) + 1;
     if (carve > 100) carve = 100;
-    for (const void *fn : {k->fn, k->fn_exact}) {
+    for (const void *fn : {k->fn, k->fn_exact, k->fn_grid}) {
         e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         if (e != cudaSuccess) return set_err(e, "cudaFuncSetAttribute(carveout)");
     }
@@ -250,6 +256,7 @@ int check_params(const dart_se3mpc_params *p)
     if (p->horizon < 1 || p->horizon > 64) return DART_E_UNSUPPORTED;
     if (p->max_corrections < 1 || p->max_corrections > MMAX) return DART_E_UNSUPPORTED;
     if (p->max_iterations < 0 || p->max_linesearch < 0) return DART_E_BADARG;
+    if (p->gradient_mode < 0 || p->gradient_mode > 2) return DART_E_UNSUPPORTED;
     if (!(p->dt > 0.0) || !(p->mass > 0.0)) return DART_E_BADARG;
     return DART_OK;
 }
@@ -296,6 +303,8 @@ void dart_se3mpc_default_params(dart_se3mpc_params *p)
     p->w_thrust = 0.1;
     p->gtol = 5e-2;             /* :68, :264 */
     p->ftol = 5e-1;             /* :265 */
+    p->w_obstacle = 1000.0;     /* obstacle_weight :60 (unused by the reference solve) */
+    p->obstacle_free_level = 0.5; /* the mapper's prior, explicit_geometric_mapper.py:71 */
 }
 
 int dart_se3mpc_kernel_info(const dart_se3mpc_params *params, int64_t B, int32_t *lanes,
@@ -324,7 +333,7 @@ static int launch_solve(const dart_se3mpc_params *params, const SolveArgs &a, vo
     SolveArgs args_copy = a;
     void *args[] = {(void *)&P, (void *)&args_copy};
     const long long grid_blocks = grid_for(*k, a.B);
-    const void *fn = params->gradient_mode == 1 ? k->fn_exact : k->fn;
+    const void *fn = params->gradient_mode == 1 ? k->fn_exact : (params->gradient_mode == 2 ? k->fn_grid : k->fn);
     cudaError_t e = cudaLaunchKernel(fn, dim3((unsigned)grid_blocks), dim3(k->block), args,
                                      smem_bytes(*k), (cudaStream_t)cuda_stream);
     if (e != cudaSuccess) return set_err(e, "cudaLaunchKernel(se3mpc_solve)");
@@ -344,7 +353,8 @@ int dart_se3mpc_solve_batch_map(const dart_se3mpc_params *params, int64_t B, int
     int rc = check_params(params);
     if (rc) return rc;
     if (B < 0 || ld < B || !p0 || !v0 || !goal) return DART_E_BADARG;
-    if (first_hit && (!grid || !grid->occ || grid->nx <= 0 || grid->ny <= 0 || grid->nz <= 0 ||
+    const bool need_grid = first_hit != nullptr || params->gradient_mode == 2;
+    if (need_grid && (!grid || !grid->occ || grid->nx <= 0 || grid->ny <= 0 || grid->nz <= 0 ||
                       !(grid->resolution > 0.0)))
         return DART_E_BADARG;
     if (B == 0) return DART_OK;
@@ -355,8 +365,8 @@ int dart_se3mpc_solve_batch_map(const dart_se3mpc_params *params, int64_t B, int
     a.x_warm = x_warm; a.warm_mask = warm_mask;
     a.x_out = x_out; a.cost = cost; a.nit = nit; a.nfev = nfev; a.status = status; a.task = task;
     a.acc = acc; a.att = att; a.rates = rates; a.thrust = thrust;
+    if (need_grid) a.grid = *grid;
     if (first_hit) {
-        a.grid = *grid;
         a.margin = margin;
         a.threshold = threshold;
         a.first_hit = first_hit;
@@ -372,6 +382,7 @@ int dart_se3mpc_closed_loop_step(const dart_se3mpc_params *params, int64_t B, in
     int rc = check_params(params);
     if (rc) return rc;
     if (B < 0 || ld < B || !p || !v || !goal || !x || !(plant_dt > 0.0)) return DART_E_BADARG;
+    if (params->gradient_mode == 2) return DART_E_UNSUPPORTED; /* no map argument here */
     if (B == 0) return DART_OK;
     SolveArgs a;
     memset(&a, 0, sizeof(a));

@@ -363,7 +363,8 @@ def plan_batch(positions, velocities, goals, config: Optional[SE3MPCConfig] = No
                mass: float = 1.5, gravity: float = 9.81, dt: Optional[float] = None,
                has_goal=None, x_warm=None, warm_mask=None, gradient_mode: int = 0,
                device=None, outputs: str = "all", to_host: bool = False, grid=None,
-               safety_margin: float = 1.0, collision_threshold: float = 0.6):
+               safety_margin: float = 1.0, collision_threshold: float = 0.6,
+               obstacle_penalty: bool = False):
     """Solve B independent SE(3)-MPC problems in one call.
 
     positions, velocities, goals : (B, 3) array-likes (NumPy or torch, host or device)
@@ -373,10 +374,18 @@ def plan_batch(positions, velocities, goals, config: Optional[SE3MPCConfig] = No
     x_warm : (B, 9N) previous solutions for warm starts (se3_mpc_planner.py:294-327)
     grid   : DenseOccupancyGrid; adds the fused post-hoc `is_trajectory_safe` check of every
              solved trajectory (result.first_hit / result.safe)
+    obstacle_penalty : with a grid, also add the occupancy-grid obstacle penalty to the objective
+             and gradient inside the solve (gradient_mode 2; extension -- the reference solve has
+             no obstacle term; weight = config.obstacle_weight, free level = the grid's prior)
     Returns a BatchSolution (device) or HostSolution (``to_host=True``).
     """
     cfg = config or SE3MPCConfig()
-    params = make_params(cfg, mass=mass, gravity=gravity, dt=dt, gradient_mode=gradient_mode)
+    if obstacle_penalty:
+        if grid is None or gradient_mode != 0:
+            raise ValueError("obstacle_penalty needs grid= and the reference gradient mode")
+        gradient_mode = 2
+    params = make_params(cfg, mass=mass, gravity=gravity, dt=dt, gradient_mode=gradient_mode,
+                         obstacle_free_level=grid.prob_prior if grid is not None else 0.5)
     B = int(np.shape(positions)[0])
     ws = BatchWorkspace(params, B, device=device, pinned=False, outputs=outputs)
     ws.set_inputs_device(positions, velocities, goals)

@@ -51,6 +51,8 @@ typedef struct dart_se3mpc_params {
     int32_t max_fun;           /* SciPy maxfun (default 15000)                             */
     int32_t gradient_mode;     /* 0: reference gradient (:552-580, inconsistent by design) */
                                /* 1: exact gradient of :516-550 (extension, self-oracle)   */
+                               /* 2: mode 0 + occupancy-grid obstacle penalty in f and g    */
+                               /*    (extension, self-oracle; needs a grid, see _solve_batch_map) */
     int32_t reserved0;
     double dt;                 /* effective planner dt (timing_alignment.py:76-78)         */
     double mass, gravity;      /* 1.5 kg, 9.81 m/s^2 (:149-150)                            */
@@ -61,6 +63,10 @@ typedef struct dart_se3mpc_params {
     double w_pos, w_vel, w_acc, w_thrust; /* cost weights (:56-59)                          */
     double gtol;               /* convergence_tolerance (:264)                             */
     double ftol;               /* 10*convergence_tolerance (:265)                          */
+    /* gradient_mode 2 only: f += w_obstacle * sum_k max(0, o(P_k) - obstacle_free_level)^2 with
+     * o = trilinear occupancy over voxel centres.  w_obstacle = SE3MPCConfig.obstacle_weight
+     * (:60, unused by the reference solve), free level = the map's prior (0.5). */
+    double w_obstacle, obstacle_free_level;
 } dart_se3mpc_params;
 
 /* ---- occupancy grid (perception/explicit_geometric_mapper.py) on a dense device grid ----
@@ -107,7 +113,9 @@ int dart_se3mpc_solve_batch(const dart_se3mpc_params *params, int64_t B, int64_t
  * (explicit_geometric_mapper.py:195-219; as the callers use it after planning,
  * cloud/main_improved_se3.py:128-130) on the N solved positions of every problem, inside the
  * solve kernel (positions never leave registers).  first_hit [ld] int32: index of the first
- * colliding position, -1 = safe.  grid/first_hit may be NULL (plain solve). */
+ * colliding position, -1 = safe.  grid/first_hit may be NULL (plain solve).
+ * With params->gradient_mode == 2 the same grid also feeds the obstacle penalty inside the
+ * solve (then `grid` is required; first_hit stays optional). */
 int dart_se3mpc_solve_batch_map(const dart_se3mpc_params *params, int64_t B, int64_t ld,
                                 const double *p0, const double *v0, const double *goal,
                                 const uint8_t *has_goal, const double *x_warm,

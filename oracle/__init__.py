@@ -165,7 +165,9 @@ class BatchResult:
         return self.x[:, 6 * N:].reshape(-1, N, 3)
 
 
-def solve_batch(p: Params, p0, v0, goal, has_goal=None, x_warm=None, nthreads=1) -> BatchResult:
+def solve_batch(p: Params, p0, v0, goal, has_goal=None, x_warm=None, nthreads=1, grid=None,
+                obstacle_weight=0.0, free_level=0.5) -> BatchResult:
+    """grid: DenseGrid -> adds the occupancy-grid obstacle penalty (extension, self-oracle)."""
     p0 = np.ascontiguousarray(p0, dtype=np.float64).reshape(-1, 3)
     B = p0.shape[0]
     v0 = np.ascontiguousarray(v0, dtype=np.float64).reshape(B, 3)
@@ -189,11 +191,15 @@ def solve_batch(p: Params, p0, v0, goal, has_goal=None, x_warm=None, nthreads=1)
     rates = np.zeros((B, N, 3))
     thrust = np.zeros((B, N))
     fl = C.c_double(0.0)
-    rc = lib().orc_solve_batch(
-        C.byref(p), B, _dp(p0), _dp(v0), _dp(goal),
+    L = lib()
+    L.orc_solve_batch_grid.restype = C.c_int
+    rc = L.orc_solve_batch_grid(
+        C.byref(p), C.c_int64(B), _dp(p0), _dp(v0), _dp(goal),
         hg.ctypes.data_as(C.POINTER(C.c_uint8)) if hg is not None else None, _dp(xw), _dp(x),
         _dp(cost), _ip(nit), _ip(nfev), _ip(status), _ip(task), _dp(acc), _dp(att), _dp(rates),
-        _dp(thrust), C.byref(fl), int(nthreads))
+        _dp(thrust), C.byref(fl), C.c_int(int(nthreads)),
+        C.byref(grid.g) if grid is not None else None, C.c_double(float(obstacle_weight)),
+        C.c_double(float(free_level)))
     if rc != 0:
         raise RuntimeError(f"orc_solve_batch failed: {rc}")
     return BatchResult(x, cost, nit, nfev, status, task, acc, att, rates, thrust, fl.value)
@@ -283,6 +289,16 @@ class DenseGrid:
     def query(self, pos):
         pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
         return np.array([lib().orc_query(C.byref(self.g), _dp(q)) for q in pos])
+
+    def penalty(self, pos, weight, free_level=0.5):
+        """(f, grad[3]) of the obstacle penalty at one position (orc_grid_penalty)."""
+        L = lib()
+        L.orc_grid_penalty.restype = C.c_double
+        q = np.ascontiguousarray(pos, dtype=np.float64).reshape(3)
+        g = np.zeros(3)
+        f = L.orc_grid_penalty(C.byref(self.g), C.c_double(float(weight)), C.c_double(float(free_level)),
+                               _dp(q), _dp(g))
+        return f, g
 
     def traj_safe(self, positions, margin, threshold):
         q = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1, 3)

@@ -206,20 +206,90 @@ void orc_extract(const orc_params *p, const double *x, double *acc, double *att,
 typedef struct {
     const orc_params *p;
     const double *goal;
+    const orc_grid *grid; /* NULL: no obstacle penalty */
+    double w_obs, free_level;
 } fg_ctx;
+
+static double grid_cell(const orc_grid *g, int kx, int ky, int kz)
+{
+    const int ix = kx - g->ox, iy = ky - g->oy, iz = kz - g->oz;
+    if (ix < 0 || iy < 0 || iz < 0 || ix >= g->nx || iy >= g->ny || iz >= g->nz) return g->prior;
+    return (double)g->occ[((int64_t)iz * g->ny + iy) * g->nx + ix];
+}
+
+/* Occupancy-grid obstacle penalty (EXTENSION -- the reference solve has no obstacle term, SURVEY
+ * 0.3; parity unpinned, this is the definition both the kernel and this oracle follow):
+ *   o(p)  = trilinear interpolation of the occupancy over voxel CENTRES ((k+0.5)*res)
+ *   rho   = max(0, o(p) - free_level)
+ *   f_obs = w * rho^2,   grad = 2 w rho * grad o(p)
+ * summed over the N positions of the horizon. */
+double orc_grid_penalty(const orc_grid *g, double w, double free_level, const double *p, double *grad)
+{
+    double u[3], t[3];
+    int i[3];
+    for (int c = 0; c < 3; ++c) {
+        u[c] = p[c] / g->resolution - 0.5;
+        const double fl = floor(u[c]);
+        i[c] = (int)fl;
+        t[c] = u[c] - fl;
+    }
+    const double c000 = grid_cell(g, i[0], i[1], i[2]), c100 = grid_cell(g, i[0] + 1, i[1], i[2]);
+    const double c010 = grid_cell(g, i[0], i[1] + 1, i[2]), c110 = grid_cell(g, i[0] + 1, i[1] + 1, i[2]);
+    const double c001 = grid_cell(g, i[0], i[1], i[2] + 1), c101 = grid_cell(g, i[0] + 1, i[1], i[2] + 1);
+    const double c011 = grid_cell(g, i[0], i[1] + 1, i[2] + 1), c111 = grid_cell(g, i[0] + 1, i[1] + 1, i[2] + 1);
+    const double sx = 1.0 - t[0], sy = 1.0 - t[1], sz = 1.0 - t[2];
+    const double c00 = c000 * sx + c100 * t[0], c10 = c010 * sx + c110 * t[0];
+    const double c01 = c001 * sx + c101 * t[0], c11 = c011 * sx + c111 * t[0];
+    const double c0 = c00 * sy + c10 * t[1], c1 = c01 * sy + c11 * t[1];
+    const double o = c0 * sz + c1 * t[2];
+    const double rho = o - free_level;
+    grad[0] = grad[1] = grad[2] = 0.0;
+    if (!(rho > 0.0)) return 0.0;
+    const double d00 = c100 - c000, d10 = c110 - c010, d01 = c101 - c001, d11 = c111 - c011;
+    const double gx = ((d00 * sy + d10 * t[1]) * sz + (d01 * sy + d11 * t[1]) * t[2]) / g->resolution;
+    const double gy = ((c10 - c00) * sz + (c11 - c01) * t[2]) / g->resolution;
+    const double gz = (c1 - c0) / g->resolution;
+    const double k = 2.0 * w * rho;
+    grad[0] = k * gx;
+    grad[1] = k * gy;
+    grad[2] = k * gz;
+    return w * (rho * rho);
+}
 
 static double planner_fg(int n, const double *x, double *g, void *user)
 {
     (void)n;
     fg_ctx *c = (fg_ctx *)user;
     orc_gradient(c->p, x, c->goal, g);
-    return orc_objective(c->p, x, c->goal);
+    double f = orc_objective(c->p, x, c->goal);
+    if (c->grid) {
+        const int N = c->p->horizon;
+        for (int k = 0; k < N; ++k) {
+            double gr[3];
+            f += orc_grid_penalty(c->grid, c->w_obs, c->free_level, x + 3 * k, gr);
+            for (int a = 0; a < 3; ++a) g[3 * k + a] += gr[a];
+        }
+    }
+    return f;
 }
 
 /* se3_mpc_planner.py:230-280 (_solve_se3_mpc) */
+static int solve_impl(const orc_params *p, const double *p0, const double *v0, const double *goal,
+                      const double *x_warm, double *x, double *acc, double *att, double *rates,
+                      double *thrust, orc_stats *st, const orc_grid *grid, double w_obs,
+                      double free_level);
+
 int orc_solve(const orc_params *p, const double *p0, const double *v0, const double *goal,
               const double *x_warm, double *x, double *acc, double *att, double *rates,
               double *thrust, orc_stats *st)
+{
+    return solve_impl(p, p0, v0, goal, x_warm, x, acc, att, rates, thrust, st, NULL, 0.0, 0.0);
+}
+
+static int solve_impl(const orc_params *p, const double *p0, const double *v0, const double *goal,
+                      const double *x_warm, double *x, double *acc, double *att, double *rates,
+                      double *thrust, orc_stats *st, const orc_grid *grid, double w_obs,
+                      double free_level)
 {
     const int N = p->horizon, n = 9 * N;
     double *lo = (double *)malloc(sizeof(double) * 2 * n);
@@ -236,7 +306,7 @@ int orc_solve(const orc_params *p, const double *p0, const double *v0, const dou
         orc_cold_start(p, p0, v0, goal, x);
     orc_bounds(p, lo, hi);
     for (int i = 0; i < n; ++i) nbd[i] = 2;
-    fg_ctx ctx = {p, goal};
+    fg_ctx ctx = {p, goal, grid, w_obs, free_level};
     const double eps = 2.220446049250313e-16;
     /* per-evaluation cost of the reference objective + gradient (48N+10, 12N) */
     int rc = orc_lbfgsb(n, p->max_corrections, x, lo, hi, nbd, planner_fg, &ctx, p->ftol / eps,
@@ -257,6 +327,8 @@ typedef struct {
     int32_t *nit, *nfev, *status, *task;
     double flops;
     int rc;
+    const orc_grid *grid;
+    double w_obs, free_level;
 } batch_job;
 
 static void *batch_worker(void *arg)
@@ -275,8 +347,8 @@ static void *batch_worker(void *arg)
         orc_stats st;
         const double *goal = (j->has_goal && !j->has_goal[b]) ? NULL : j->goal + 3 * b;
         const double *xw = j->x_warm ? j->x_warm + (int64_t)n * b : NULL;
-        int rc = orc_solve(j->p, j->p0 + 3 * b, j->v0 + 3 * b, goal, xw, x, acc, att, rates, thrust,
-                           &st);
+        int rc = solve_impl(j->p, j->p0 + 3 * b, j->v0 + 3 * b, goal, xw, x, acc, att, rates, thrust,
+                            &st, j->grid, j->w_obs, j->free_level);
         if (rc) j->rc = rc;
         j->flops += st.flops;
         if (j->x) memcpy(j->x + (int64_t)n * b, x, sizeof(double) * n);
@@ -300,6 +372,17 @@ int orc_solve_batch(const orc_params *p, int64_t B, const double *p0, const doub
                     int32_t *task, double *acc, double *att, double *rates, double *thrust,
                     double *flops_total, int nthreads)
 {
+    return orc_solve_batch_grid(p, B, p0, v0, goal, has_goal, x_warm, x, cost, nit, nfev, status, task,
+                                acc, att, rates, thrust, flops_total, nthreads, NULL, 0.0, 0.0);
+}
+
+int orc_solve_batch_grid(const orc_params *p, int64_t B, const double *p0, const double *v0,
+                         const double *goal, const uint8_t *has_goal, const double *x_warm,
+                         double *x, double *cost, int32_t *nit, int32_t *nfev, int32_t *status,
+                         int32_t *task, double *acc, double *att, double *rates, double *thrust,
+                         double *flops_total, int nthreads, const orc_grid *grid, double w_obs,
+                         double free_level)
+{
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 256) nthreads = 256;
     if ((int64_t)nthreads > B) nthreads = B > 0 ? (int)B : 1;
@@ -319,6 +402,7 @@ int orc_solve_batch(const orc_params *p, int64_t B, const double *p0, const doub
         j->p0 = p0; j->v0 = v0; j->goal = goal; j->x_warm = x_warm; j->has_goal = has_goal;
         j->x = x; j->cost = cost; j->acc = acc; j->att = att; j->rates = rates; j->thrust = thrust;
         j->nit = nit; j->nfev = nfev; j->status = status; j->task = task;
+        j->grid = grid; j->w_obs = w_obs; j->free_level = free_level;
         if (nthreads == 1)
             batch_worker(j);
         else if (pthread_create(&th[t], NULL, batch_worker, j) != 0) {

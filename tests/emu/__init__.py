@@ -34,7 +34,7 @@ class Result:
     pass
 
 
-def solve_batch(params, p0, v0, goal, has_goal=None, x_warm=None):
+def solve_batch(params, p0, v0, goal, has_goal=None, x_warm=None, grid=None):
     """params: dart_planner_b200._cabi.Params (ctypes mirror of dart_se3mpc_params)."""
     p0 = np.ascontiguousarray(p0, np.float64).reshape(-1, 3)
     B = len(p0)
@@ -54,7 +54,7 @@ def solve_batch(params, p0, v0, goal, has_goal=None, x_warm=None):
     rc = lib().emu_solve_batch(C.byref(params), C.c_long(B), vp(p0), vp(v0), vp(goal), vp(hg),
                                vp(xw), vp(r.x), vp(r.cost), vp(r.nit), vp(r.nfev), vp(r.status),
                                vp(r.task), vp(r.accelerations), vp(r.attitudes), vp(r.body_rates),
-                               vp(r.thrusts))
+                               vp(r.thrusts), None if grid is None else C.byref(grid))
     if rc != 0:
         raise RuntimeError(f"emu_solve_batch: {rc}")
     return r

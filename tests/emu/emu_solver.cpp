@@ -14,13 +14,19 @@ using namespace dartb200;
 template <int TPL, int GM>
 static void solve_one(const dart_se3mpc_params &P, const double *p0, const double *v0,
                       const double *goal, int has_goal, const double *xw, double *x_out,
-                      double *acc, double *att, double *rates, double *thrust, SolveStats &st)
+                      double *acc, double *att, double *rates, double *thrust, SolveStats &st,
+                      const dart_grid *grid)
 {
     double smem[SM_DOUBLES];
     for (int i = 0; i < SM_DOUBLES; ++i) smem[i] = 0.0 / 0.0; /* NaN-poison: catches stale reads */
     static double ws[MMAX][9 * TPL], wy[MMAX][9 * TPL];
     Solver<SeqGroup, TPL, GM> sv(P, smem, ws, wy);
     const int N = P.horizon;
+    if (GM == 2) {
+        sv.obs.g = *grid;
+        sv.obs.w = P.w_obstacle;
+        sv.obs.free_level = P.obstacle_free_level;
+    }
     sv.has_goal = has_goal != 0;
     for (int c = 0; c < 3; ++c) sv.goal[c] = goal[c];
     if (xw)
@@ -43,17 +49,18 @@ extern "C" int emu_solve_batch(const dart_se3mpc_params *P, long B, const double
                                const double *v0, const double *goal, const unsigned char *has_goal,
                                const double *x_warm, double *x, double *cost, int *nit, int *nfev,
                                int *status, int *task, double *acc, double *att, double *rates,
-                               double *thrust)
+                               double *thrust, const dart_grid *grid)
 {
     const int N = P->horizon, n = 9 * N;
     if (N < 1 || N > 32 || P->max_corrections < 1 || P->max_corrections > MMAX) return -2;
+    if (P->gradient_mode == 2 && !grid) return -1;
     for (long b = 0; b < B; ++b) {
         SolveStats st;
         const double *xw = x_warm ? x_warm + (long)n * b : nullptr;
         const int hg = has_goal ? has_goal[b] : 1;
 #define CALL1(T, GM) solve_one<T, GM>(*P, p0 + 3 * b, v0 + 3 * b, goal + 3 * b, hg, xw, x + (long)n * b, \
-                             acc + 3L * N * b, att + 3L * N * b, rates + 3L * N * b, thrust + (long)N * b, st)
-#define CALL(T) do { if (P->gradient_mode == 1) CALL1(T, 1); else CALL1(T, 0); } while (0)
+                             acc + 3L * N * b, att + 3L * N * b, rates + 3L * N * b, thrust + (long)N * b, st, grid)
+#define CALL(T) do { if (P->gradient_mode == 1) CALL1(T, 1); else if (P->gradient_mode == 2) CALL1(T, 2); else CALL1(T, 0); } while (0)
         if (N <= 8) CALL(8);
         else if (N <= 20) CALL(20);
         else CALL(32);

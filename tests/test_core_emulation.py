@@ -38,3 +38,37 @@ def test_core_matches_oracle_random(oracle_mod):
         assert same.mean() > 0.999, f"counter mismatches: {np.where(~same)[0][:10]}"
         dx = np.abs(got.x - ref.x).max(axis=1)
         assert (dx[same] < 1e-6).all()
+
+
+def _penalty_world(oracle_mod, seed=7):
+    rng = np.random.default_rng(seed)
+    og = oracle_mod.DenseGrid((128, 128, 128), (-64, -64, -64), 0.4)
+    for c, r in zip(rng.uniform(-15, 15, (48, 3)), rng.uniform(0.8, 2.5, 48)):
+        og.add_sphere(c, r)
+    return og
+
+
+def test_core_grid_penalty_mode_matches_oracle(oracle_mod):
+    """gradient_mode 2 (extension, self-oracle): reference gradient + occupancy-grid penalty."""
+    import emu
+    from dart_planner_b200 import _cabi
+    from dart_planner_b200.config import SE3MPCConfig, make_params
+    og = _penalty_world(oracle_mod)
+    grid = _cabi.Grid(128, 128, 128, -64, -64, -64, 0.4, 0.5, og.occ.ctypes.data)
+    rng = np.random.default_rng(5)
+    B = 1500
+    p0 = rng.uniform(-10, 10, (B, 3))
+    v0 = rng.uniform(-2, 2, (B, 3))
+    goal = np.concatenate([rng.uniform(-15, 15, (B, 2)), rng.uniform(3, 8, (B, 1))], axis=1)
+    for N, dt, w in ((8, 0.1, 1000.0), (6, 0.0025, 250.0)):
+        cfg = SE3MPCConfig(prediction_horizon=N, dt=dt, obstacle_weight=w)
+        ref = oracle_mod.solve_batch(oracle_mod.make_params(horizon=N, dt=dt), p0, v0, goal, nthreads=8,
+                                     grid=og, obstacle_weight=w, free_level=0.5)
+        plain = oracle_mod.solve_batch(oracle_mod.make_params(horizon=N, dt=dt), p0, v0, goal, nthreads=8)
+        assert (np.abs(ref.x - plain.x).max(axis=1) > 1e-6).mean() > 0.1       # the penalty matters
+        got = emu.solve_batch(make_params(cfg, gradient_mode=2), p0, v0, goal, grid=grid)
+        same = (got.nit == ref.nit) & (got.nfev == ref.nfev) & (got.status == ref.status)
+        assert same.mean() > 0.995, f"counter mismatches: {np.where(~same)[0][:10]}"
+        assert (np.abs(got.x - ref.x).max(axis=1)[same] < 1e-6).all()
+        relf = np.abs(got.cost - ref.cost) / np.maximum(np.abs(ref.cost), 1.0)
+        assert (relf[same] < 1e-9).all()

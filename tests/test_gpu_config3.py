@@ -78,3 +78,38 @@ def test_fused_safety_other_horizons(oracle_mod):
         host = sol.numpy()
         own = np.array([og.traj_safe(host.positions[i], 1.0, 0.6) for i in range(512)])
         np.testing.assert_array_equal(host.first_hit, own)
+
+
+def test_grid_penalty_mode_matches_self_oracle(oracle_mod):
+    """BASELINE configs[2] 'with mapper obstacle cost': gradient_mode 2 adds the occupancy-grid
+    penalty to f and g inside the solve.  The reference computes no obstacle term,
+    so this is an extension checked against our own CPU restatement (self-oracle)."""
+    import dart_planner_b200 as dp
+    centers, radii = config3_world()
+    grid = dp.DenseOccupancyGrid((256, 256, 256), (-128, -128, -128), 0.2)
+    grid.add_obstacles(centers, radii)
+    og = oracle_mod.DenseGrid((256, 256, 256), (-128, -128, -128), 0.2)
+    for c, r in zip(centers, radii):
+        og.add_sphere(c, r)
+    B = 16384
+    p0, v0, goal = config3_inputs(2, B)
+    cfg = dp.SE3MPCConfig(prediction_horizon=8, dt=0.1)
+    sol = dp.plan_batch(p0, v0, goal, cfg, grid=grid, safety_margin=1.5, collision_threshold=0.6,
+                        obstacle_penalty=True)
+    host = sol.numpy()
+    ref = oracle_mod.solve_batch(oracle_mod.make_params(horizon=8, dt=0.1), p0, v0, goal, nthreads=16,
+                                 grid=og, obstacle_weight=cfg.obstacle_weight, free_level=0.5)
+    plain = dp.plan_batch(p0, v0, goal, cfg, to_host=True)
+    changed = np.abs(host.x - plain.x).max(axis=1) > 1e-6
+    assert changed.mean() > 0.05                      # the penalty is active for part of the batch
+    same = (host.nit == ref.nit) & (host.nfev == ref.nfev) & (host.status == ref.status)
+    assert same.mean() >= 0.995, f"counters agree on {same.mean():.4f}"
+    relf = np.abs(host.cost - ref.cost) / np.maximum(np.abs(ref.cost), 1.0)
+    dx = np.abs(host.x - ref.x).max(axis=1)
+    assert (relf[same] <= 1e-5).all() and (dx[same] <= 1e-4).all()
+    # the penalised solutions collide less often than the plain ones (sanity of the definition)
+    hit_plain = grid.trajectories_safe_soa(dp.plan_batch(p0, v0, goal, cfg).out, B, 8, 1.5, 0.6)[:B].cpu().numpy()
+    assert (host.first_hit >= 0).sum() <= (hit_plain >= 0).sum()
+    # penalty mode without a grid is rejected
+    with pytest.raises(ValueError):
+        dp.plan_batch(p0[:4], v0[:4], goal[:4], cfg, obstacle_penalty=True)

@@ -361,6 +361,49 @@ def main():
                                "e2e_value": Bs / (statistics.mean(m2) * 1e-3)}
             del w2
         line["sweep"] = sweep
+        # the other BASELINE configs, timed once each (kernel-only, resident inputs); their
+        # parity lives in tests/test_gpu_config3.py and tests/test_gpu_closed_loop.py
+        others = {}
+        rng = np.random.default_rng(2)
+        grid = dp.DenseOccupancyGrid((256, 256, 256), (-128, -128, -128), 0.2)
+        grid.add_obstacles(rng.uniform(-20, 20, (64, 3)), rng.uniform(0.5, 2.0, 64))
+        Bs = 65536
+        a0, b0, c0 = workload_inputs(Bs, 2)
+        b0 = np.random.default_rng(22).uniform(-2, 2, (Bs, 3))
+        w3 = BatchWorkspace(params, Bs, pinned=False, outputs="all")
+        w3.set_inputs_device(a0, b0, c0)
+        w3.set_map(grid, 1.5, 0.6)
+        m3 = time_steps(torch, lambda: w3.solve_device(stream), flush, 10, 3, stream)
+        unsafe = float((w3.hit[:Bs] >= 0).float().mean().item())
+        others["configs[2] 65536 solves + fused is_trajectory_safe on a 256^3 grid"] = {
+            "value": Bs / (statistics.mean(m3) * 1e-3), "unit": UNIT, "kernel_ms": statistics.mean(m3),
+            "unsafe_fraction": unsafe}
+        p2 = make_params(cfg, gradient_mode=2)
+        w3p = BatchWorkspace(p2, Bs, pinned=False, outputs="all")
+        w3p.set_inputs_device(a0, b0, c0)
+        w3p.set_map(grid, 1.5, 0.6)
+        m3p = time_steps(torch, lambda: w3p.solve_device(stream), flush, 10, 3, stream)
+        others["configs[2] same with the occupancy-grid obstacle penalty in the solve (extension, self-oracle)"] = {
+            "value": Bs / (statistics.mean(m3p) * 1e-3), "unit": UNIT, "kernel_ms": statistics.mean(m3p),
+            "unsafe_fraction": float((w3p.hit[:Bs] >= 0).float().mean().item())}
+        del w3, w3p
+        from dart_planner_b200.closed_loop import ClosedLoopSim
+        sim = ClosedLoopSim(params, Bs, plant_dt=args.dt)
+        a4, _, c4 = workload_inputs(Bs, 4)
+        b4 = np.random.default_rng(44).uniform(-2, 2, (Bs, 3))
+        sim.reset(a4, b4, c4)
+        sim.run(3, stream, track_counters=False)
+        sim.reset(a4, b4, c4)
+        torch.cuda.synchronize()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record(stream)
+        sim.run(100, stream, track_counters=False)
+        eb.record(stream)
+        torch.cuda.synchronize()
+        cl_ms = ea.elapsed_time(eb)
+        others["configs[4] closed loop: 65536 drones x 100 replans (10 s at 10 Hz), warm starts, resident state"] = {
+            "value": Bs * 100 / (cl_ms * 1e-3), "unit": UNIT, "total_ms": cl_ms, "launches": 100}
+        line["other_configs"] = others
         # single-solve latency through the drop-in planner (metric's second half)
         planner = dp.SE3MPCPlanner.from_yaml()
         st = dp.DroneState(0.0, np.array([0.0, 0.0, 2.0]))

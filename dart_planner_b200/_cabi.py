@@ -55,7 +55,7 @@ EXPORTS = [
     "dart_se3mpc_solve_batch_host",
     "dart_launch_count",
     "dart_se3mpc_kernel_info", "dart_map_query_batch", "dart_map_traj_safe_batch",
-    "dart_map_trace_ray_batch", "dart_map_add_spheres", "dart_fp64_probe",
+    "dart_map_trace_ray_batch", "dart_map_update_batch", "dart_map_add_spheres", "dart_fp64_probe",
 ]
 
 _lib = None
@@ -100,6 +100,9 @@ def lib():
     L.dart_map_traj_safe_batch.restype = C.c_int
     L.dart_map_trace_ray_batch.argtypes = [C.c_double, i64, i64, vp, vp, vp, i32, vp, vp, vp]
     L.dart_map_trace_ray_batch.restype = C.c_int
+    L.dart_map_update_batch.argtypes = [C.POINTER(Grid), vp, vp, i64, i64, vp, vp, vp, vp, C.c_double,
+                                        C.c_double, C.c_double, vp, vp]
+    L.dart_map_update_batch.restype = C.c_int
     L.dart_map_add_spheres.argtypes = [C.POINTER(Grid), vp, i32, vp, vp, C.c_float, vp]
     L.dart_map_add_spheres.restype = C.c_int
     L.dart_fp64_probe.argtypes = [i32, C.POINTER(i32), vp, vp]

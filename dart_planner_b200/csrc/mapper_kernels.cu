@@ -52,69 +52,149 @@ map_traj_safe_kernel(const __grid_constant__ dart_grid g, long long B, long long
 }
 
 /* _trace_ray: Amanatides-Woo DDA with the reference's quirks (step from voxel indices,
- * tie -> lowest axis, loop while cur != end and total <= dist) */
+ * tie -> lowest axis, loop while cur != end and total <= dist).  visit(kx, ky, kz, n) is called
+ * for every voxel in order (n = index along the ray); returns the number of voxels. */
+template <class Visit>
+__device__ __forceinline__ int dda_walk(double res, const double s[3], const double d_in[3],
+                                        double distance, Visit &&visit)
+{
+    double d[3], tdelta[3], tmax[3];
+    int cur[3], endv[3], step[3];
+    const double nrm = sqrt((d_in[0] * d_in[0] + d_in[1] * d_in[1]) + d_in[2] * d_in[2]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        d[c] = d_in[c] / nrm;
+        const double e = s[c] + d[c] * distance;
+        cur[c] = vox(s[c], res);
+        endv[c] = vox(e, res);
+    }
+    int n = 0;
+    visit(cur[0], cur[1], cur[2], n);
+    ++n;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        step[c] = endv[c] > cur[c] ? 1 : (endv[c] < cur[c] ? -1 : 0);
+        if (step[c] != 0) {
+            tdelta[c] = res / fabs(d[c]);
+            const double boundary = (double)(cur[c] + (step[c] > 0 ? 1 : 0)) * res;
+            tmax[c] = fabs((boundary - s[c]) / d[c]);
+        } else {
+            tdelta[c] = INFINITY;
+            tmax[c] = INFINITY;
+        }
+    }
+    double total = 0.0;
+    while ((cur[0] != endv[0] || cur[1] != endv[1] || cur[2] != endv[2]) && total <= distance) {
+        int axis = 0;
+        if (tmax[1] < tmax[axis]) axis = 1;
+        if (tmax[2] < tmax[axis]) axis = 2;
+        /* register-friendly select instead of dynamic indexing */
+        if (axis == 0) {
+            cur[0] += step[0]; total = tmax[0]; tmax[0] += tdelta[0];
+        } else if (axis == 1) {
+            cur[1] += step[1]; total = tmax[1]; tmax[1] += tdelta[1];
+        } else {
+            cur[2] += step[2]; total = tmax[2]; tmax[2] += tdelta[2];
+        }
+        visit(cur[0], cur[1], cur[2], n);
+        ++n;
+        if (n > (1 << 24)) break; /* NaN guard */
+    }
+    return n;
+}
+
 __global__ void __launch_bounds__(256)
 map_trace_ray_kernel(double res, long long B, long long ld, const double *start, const double *dir,
                      const double *dist, int max_vox, int *count, int *voxels)
 {
     for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B;
          b += (long long)gridDim.x * blockDim.x) {
-        double s[3], d[3], tdelta[3], tmax[3];
-        int cur[3], endv[3], step[3];
+        double s[3], d[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             s[c] = __ldg(start + c * ld + b);
             d[c] = __ldg(dir + c * ld + b);
         }
-        const double distance = __ldg(dist + b);
-        const double nrm = sqrt((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            d[c] = d[c] / nrm;
-            const double e = s[c] + d[c] * distance;
-            cur[c] = vox(s[c], res);
-            endv[c] = vox(e, res);
-        }
-        int n = 0;
-        auto emit = [&](void) {
+        count[b] = dda_walk(res, s, d, __ldg(dist + b), [&](int kx, int ky, int kz, int n) {
             if (voxels && n < max_vox) {
                 int *v = voxels + ((long long)n * 3) * ld + b;
-                v[0] = cur[0];
-                v[ld] = cur[1];
-                v[2 * ld] = cur[2];
+                v[0] = kx;
+                v[ld] = ky;
+                v[2 * ld] = kz;
             }
-            ++n;
-        };
-        emit();
+        });
+    }
+}
+
+/* update_map (:100-152), pass 1: one thread per observation walks its ray and COUNTS the visits
+ * per voxel (misses in the low word, endpoint hits in the high word of a 64-bit counter) with
+ * atomics -- integer, hence independent of the order rays are processed in.  Pass 2 applies
+ * the Bayes rule (:311-336) that many times.  The reference applies the same updates in
+ * observation order; both likelihoods raise the odds (the reference's miss likelihood is
+ * 1 - prob_miss = 0.6) and the clip at 0.99 is a fixed point, so the result is
+ * order-independent up to rounding. */
+__global__ void __launch_bounds__(256)
+map_update_rays_kernel(const __grid_constant__ dart_grid g, long long B, long long ld,
+                       const double *start, const double *dir, const double *hit,
+                       const double *obs_max_range, double mapper_max_range,
+                       unsigned long long *counts, unsigned long long *updated_total)
+{
+    long long visits = 0;
+    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B;
+         b += (long long)gridDim.x * blockDim.x) {
+        double s[3], d[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            step[c] = endv[c] > cur[c] ? 1 : (endv[c] < cur[c] ? -1 : 0);
-            if (step[c] != 0) {
-                tdelta[c] = res / fabs(d[c]);
-                const double boundary = (double)(cur[c] + (step[c] > 0 ? 1 : 0)) * res;
-                tmax[c] = fabs((boundary - s[c]) / d[c]);
-            } else {
-                tdelta[c] = INFINITY;
-                tmax[c] = INFINITY;
-            }
+            s[c] = __ldg(start + c * ld + b);
+            d[c] = __ldg(dir + c * ld + b);
         }
-        double total = 0.0;
-        while ((cur[0] != endv[0] || cur[1] != endv[1] || cur[2] != endv[2]) && total <= distance) {
-            int axis = 0;
-            if (tmax[1] < tmax[axis]) axis = 1;
-            if (tmax[2] < tmax[axis]) axis = 2;
-            /* register-friendly select instead of dynamic indexing */
-            if (axis == 0) {
-                cur[0] += step[0]; total = tmax[0]; tmax[0] += tdelta[0];
-            } else if (axis == 1) {
-                cur[1] += step[1]; total = tmax[1]; tmax[1] += tdelta[1];
-            } else {
-                cur[2] += step[2]; total = tmax[2]; tmax[2] += tdelta[2];
-            }
-            emit();
-            if (n > (1 << 24)) break; /* NaN guard */
-        }
-        count[b] = n;
+        const double h = __ldg(hit + b);
+        const bool none = isnan(h);
+        double hd = (none || h == 0.0) ? __ldg(obs_max_range + b) : h; /* falsy -> max_range (:112) */
+        hd = fmin(hd, mapper_max_range);
+        /* the last voxel is only known when the walk ends: count every voxel as a miss, then
+         * move the last one to the hit word if the observation had a return */
+        long long last = -1;
+        const int n = dda_walk(g.resolution, s, d, hd, [&](int kx, int ky, int kz, int) {
+            const int ix = kx - g.ox, iy = ky - g.oy, iz = kz - g.oz;
+            last = -1;
+            if (ix < 0 || iy < 0 || iz < 0 || ix >= g.nx || iy >= g.ny || iz >= g.nz) return;
+            last = ((long long)iz * g.ny + iy) * g.nx + ix;
+            atomicAdd(counts + last, 1ull);
+        });
+        if (!none && last >= 0) atomicAdd(counts + last, (1ull << 32) - 1ull); /* -1 miss, +1 hit */
+        visits += n;
+    }
+    /* block-level sum of the visit counter, one atomic per warp */
+    for (int o = 16; o > 0; o >>= 1) visits += __shfl_xor_sync(0xffffffffu, visits, o);
+    if ((threadIdx.x & 31) == 0 && updated_total && visits) atomicAdd(updated_total, (unsigned long long)visits);
+}
+
+__device__ __forceinline__ double bayes_update(double p, double lik)
+{
+    const double num = lik * p;
+    const double den = lik * p + (1.0 - lik) * (1.0 - p);
+    if (den > 0.0) p = num / den;
+    return fmin(fmax(p, 0.01), 0.99);
+}
+
+__global__ void __launch_bounds__(256)
+map_apply_counts_kernel(float *occ, unsigned long long *counts, long long ncell, double lik_hit,
+                        double lik_miss)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ncell;
+         i += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long c = counts[i];
+        if (c == 0ull) continue;
+        counts[i] = 0ull; /* leave the scratch zeroed for the next scan */
+        unsigned miss = (unsigned)(c & 0xffffffffull), hitn = (unsigned)(c >> 32);
+        double p = (double)occ[i];
+        /* 0.99 is a fixed point of both updates after the clip: 64 applications saturate */
+        if (miss > 64u) miss = 64u;
+        if (hitn > 64u) hitn = 64u;
+        for (unsigned k = 0; k < miss; ++k) p = bayes_update(p, lik_miss);
+        for (unsigned k = 0; k < hitn; ++k) p = bayes_update(p, lik_hit);
+        occ[i] = (float)p;
     }
 }
 
@@ -196,6 +276,30 @@ int dart_map_trace_ray_batch(double resolution, int64_t B, int64_t ld, const dou
     if (B == 0) return DART_OK;
     map_trace_ray_kernel<<<grid_blocks(B), 256, 0, (cudaStream_t)stream>>>(resolution, B, ld, start, dir,
                                                                           dist, max_vox, count, voxels);
+    if (cudaGetLastError() != cudaSuccess) return DART_E_CUDA;
+    dart_count_launch_();
+    return DART_OK;
+}
+
+int dart_map_update_batch(const dart_grid *g, float *occ_writable, uint64_t *counts, int64_t B,
+                          int64_t ld, const double *start, const double *dir,
+                          const double *hit_distance, const double *obs_max_range,
+                          double mapper_max_range, double prob_hit, double prob_miss,
+                          uint64_t *updated_voxels, void *stream)
+{
+    if (check_grid(g) || !occ_writable || !counts || B < 0 || ld < B || !start || !dir || !hit_distance ||
+        !obs_max_range || !(mapper_max_range > 0.0))
+        return DART_E_BADARG;
+    if (B == 0) return DART_OK;
+    map_update_rays_kernel<<<grid_blocks(B), 256, 0, (cudaStream_t)stream>>>(
+        *g, B, ld, start, dir, hit_distance, obs_max_range, mapper_max_range,
+        (unsigned long long *)counts, (unsigned long long *)updated_voxels);
+    if (cudaGetLastError() != cudaSuccess) return DART_E_CUDA;
+    dart_count_launch_();
+    const long long ncell = (long long)g->nx * g->ny * g->nz;
+    /* likelihoods exactly as _bayesian_update forms them (:322-327) */
+    map_apply_counts_kernel<<<grid_blocks(ncell), 256, 0, (cudaStream_t)stream>>>(
+        occ_writable, (unsigned long long *)counts, ncell, prob_hit, 1.0 - prob_miss);
     if (cudaGetLastError() != cudaSuccess) return DART_E_CUDA;
     dart_count_launch_();
     return DART_OK;

@@ -26,12 +26,16 @@ def _torch():
 class DenseOccupancyGrid:
     def __init__(self, shape: Tuple[int, int, int] = (256, 256, 256),
                  origin_voxel: Tuple[int, int, int] = (-128, -128, -128),
-                 resolution: float = 0.2, prior: float = 0.5, device=None):
+                 resolution: float = 0.2, prior: float = 0.5, device=None, max_range: float = 50.0):
         torch = _torch()
         self.nx, self.ny, self.nz = (int(s) for s in shape)
         self.origin_voxel = tuple(int(o) for o in origin_voxel)
         self.resolution = float(resolution)
         self.prob_prior = float(prior)
+        self.prob_hit, self.prob_miss = 0.7, 0.4        # explicit_geometric_mapper.py:80-81
+        self.max_range = float(max_range)               # :66
+        self.total_observations = 0
+        self._counts = None                              # update_map scratch (uint64 per cell)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.occ = torch.full((self.nz, self.ny, self.nx), prior, dtype=torch.float32, device=self.device)
 
@@ -116,6 +120,31 @@ class DenseOccupancyGrid:
         """Reference signature (:195-219): returns (is_safe, first_collision_index)."""
         idx = int(self.are_trajectories_safe(np.asarray(positions, float)[None], safety_margin, threshold)[0])
         return idx < 0, idx
+
+    def update_map(self, positions, directions, hit_distances, max_ranges=50.0, stream=None):
+        """Batched `update_map` (:100-152) for one scan: B observations given as arrays
+        (SensorObservation.position / direction / hit_distance / max_range; hit_distance None or
+        NaN = no return).  Two launches: ray walk with per-voxel visit counters, then the Bayes
+        rule applied per voxel.  Returns the reference's counters dict."""
+        torch = _torch()
+        start = self._soa(positions, 3)
+        d = self._soa(directions, 3)
+        B = start.shape[1]
+        hit = np.array([np.nan if h is None else float(h) for h in np.asarray(hit_distances, object).reshape(-1)])
+        hit_t = torch.as_tensor(hit, dtype=torch.float64).to(self.device)
+        mr = torch.as_tensor(np.broadcast_to(np.asarray(max_ranges, np.float64), (B,)).copy()).to(self.device)
+        if self._counts is None:
+            self._counts = torch.zeros(self.nx * self.ny * self.nz, dtype=torch.int64, device=self.device)
+        updated = torch.zeros(1, dtype=torch.int64, device=self.device)
+        g = self._grid()
+        rc = _cabi.lib().dart_map_update_batch(
+            C.byref(g), self.occ.data_ptr(), self._counts.data_ptr(), B, B, start.data_ptr(), d.data_ptr(),
+            hit_t.data_ptr(), mr.data_ptr(), self.max_range, self.prob_hit, self.prob_miss,
+            updated.data_ptr(), self._stream(stream))
+        _cabi.check(rc, "dart_map_update_batch")
+        self.total_observations += B
+        return {"updated_voxels": int(updated.item()), "observations_processed": B,
+                "total_voxels": int((self.occ != self.prob_prior).sum().item())}
 
     def trace_rays(self, starts, directions, distances, max_vox: int = 0, stream=None):
         """_trace_ray (:250-309) for B rays.  Returns (count (B,) int32, voxels (max_vox,3,B) int32

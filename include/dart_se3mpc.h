@@ -175,6 +175,19 @@ int dart_map_traj_safe_batch(const dart_grid *g, int64_t B, int64_t ld, int32_t 
 int dart_map_trace_ray_batch(double resolution, int64_t B, int64_t ld, const double *start,
                              const double *dir, const double *dist, int32_t max_vox,
                              int32_t *count, int32_t *voxels, void *cuda_stream);
+/* update_map (:100-152) for a scan of B observations (SensorObservation :40-47): start, dir
+ * [3][ld]; hit_distance [ld] (NaN = None: no return); obs_max_range [ld] (the observation's own
+ * max_range, used when hit_distance is falsy :112); mapper_max_range caps the ray (:113).
+ * Every voxel on a ray gets a Bayes "miss" update, the last one a "hit" update when there was a
+ * return (:118-135), with likelihoods prob_hit and 1 - prob_miss (:322-327) and the clip to
+ * [0.01, 0.99].  counts: caller-owned scratch of nx*ny*nz uint64, zero on entry, zero on return.
+ * updated_voxels: optional device counter, incremented by the number of voxel visits (the
+ * reference's `updated_voxels`).  Voxels outside the dense grid are visited but not stored. */
+int dart_map_update_batch(const dart_grid *g, float *occ_writable, uint64_t *counts, int64_t B,
+                          int64_t ld, const double *start, const double *dir,
+                          const double *hit_distance, const double *obs_max_range,
+                          double mapper_max_range, double prob_hit, double prob_miss,
+                          uint64_t *updated_voxels, void *cuda_stream);
 /* add_obstacle (:399-423): rasterise n spheres (centres [3][n], radii [n]) into a writable
  * grid with the reference's voxel-corner distance test; value 0.9. */
 int dart_map_add_spheres(const dart_grid *g, float *occ_writable, int32_t n,

@@ -306,6 +306,20 @@ class DenseGrid:
                                    float(threshold))
 
 
+def update_map(grid: "DenseGrid", occ64, pos, direction, hit, obs_max_range, mapper_max_range, counts=None):
+    """Sequential update_map on a double-precision copy of the grid (modified in place)."""
+    L = lib()
+    L.orc_update_map.restype = C.c_int64
+    pos = np.ascontiguousarray(pos, np.float64).reshape(-1, 3)
+    n = len(pos)
+    d = np.ascontiguousarray(direction, np.float64).reshape(n, 3)
+    h = np.ascontiguousarray(hit, np.float64).reshape(n)
+    mr = np.ascontiguousarray(obs_max_range, np.float64).reshape(n)
+    assert occ64.dtype == np.float64 and occ64.flags.c_contiguous and occ64.shape == grid.occ.shape
+    return L.orc_update_map(C.byref(grid.g), _dp(occ64), _ip(counts) if counts is not None else None,
+                            C.c_int64(n), _dp(pos), _dp(d), _dp(h), _dp(mr), C.c_double(float(mapper_max_range)))
+
+
 def trace_ray(res, start, direction, distance, max_vox=4096):
     s = np.ascontiguousarray(start, dtype=np.float64)
     d = np.ascontiguousarray(direction, dtype=np.float64)

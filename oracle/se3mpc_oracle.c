@@ -541,3 +541,42 @@ double orc_bayes(double p, int hit)
     if (p > 0.99) p = 0.99;
     return p;
 }
+
+/* :100-152 update_map, sequential like the reference (observation order, voxel order along the
+ * ray).  occ64: [nz][ny][nx] doubles (the reference stores Python floats); counts: per-cell
+ * observation_count or NULL.  Voxels outside the dense grid are walked and counted (the
+ * reference's dict would create them) but not stored.  hit[i] = NaN means hit_distance=None.
+ * Returns `updated_voxels`. */
+int64_t orc_update_map(const orc_grid *g, double *occ64, int32_t *counts, int64_t n, const double *pos,
+                       const double *dir, const double *hit, const double *obs_max_range,
+                       double mapper_max_range)
+{
+    int64_t updated = 0;
+    int cap = 1 << 16;
+    int32_t *vox = (int32_t *)malloc(sizeof(int32_t) * 3 * cap);
+    if (!vox) return -1;
+    for (int64_t i = 0; i < n; ++i) {
+        const int none = isnan(hit[i]);
+        double hd = (none || hit[i] == 0.0) ? obs_max_range[i] : hit[i]; /* falsy -> max_range (:112) */
+        if (mapper_max_range < hd) hd = mapper_max_range;
+        int cnt = orc_trace_ray(g->resolution, pos + 3 * i, dir + 3 * i, hd, vox, cap);
+        if (cnt > cap) {
+            cap = cnt;
+            free(vox);
+            vox = (int32_t *)malloc(sizeof(int32_t) * 3 * cap);
+            if (!vox) return -1;
+            cnt = orc_trace_ray(g->resolution, pos + 3 * i, dir + 3 * i, hd, vox, cap);
+        }
+        for (int k = 0; k < cnt; ++k) {
+            const int endpoint = (k == cnt - 1) && !none;
+            const int ix = vox[3 * k] - g->ox, iy = vox[3 * k + 1] - g->oy, iz = vox[3 * k + 2] - g->oz;
+            updated++;
+            if (ix < 0 || iy < 0 || iz < 0 || ix >= g->nx || iy >= g->ny || iz >= g->nz) continue;
+            const int64_t idx = ((int64_t)iz * g->ny + iy) * g->nx + ix;
+            occ64[idx] = orc_bayes(occ64[idx], endpoint);
+            if (counts) counts[idx]++;
+        }
+    }
+    free(vox);
+    return updated;
+}

@@ -69,3 +69,42 @@ def test_config3_map_against_oracle(oracle_mod):
         v, n = oracle_mod.trace_ray(0.2, starts[i], dirs[i], dist[i], max_vox=256)
         assert n == count[i]
         np.testing.assert_array_equal(vox[:n, :, i], v)
+
+
+def test_update_map_matches_reference_fixture_and_oracle(oracle_mod):
+    """Batched update_map (:100-152): two scans, against the reference mapper's resulting dict
+    (float32 grid storage -> 1e-6) and against the sequential oracle at LiDAR scale."""
+    import dart_planner_b200 as dp
+    d = load_golden("update_map")
+    keys, probs = d["keys"], d["probs"]
+    lo = keys.min(0) - 1
+    shape = tuple(int(v) for v in (keys.max(0) - lo + 2))
+    g = dp.DenseOccupancyGrid(shape, tuple(int(v) for v in lo), float(d["res"]),
+                              max_range=float(d["mapper_max_range"]))
+    s = int(d["split"])
+    r1 = g.update_map(d["pos"][:s], d["dir"][:s], d["hit"][:s], d["obs_max_range"][:s])
+    r2 = g.update_map(d["pos"][s:], d["dir"][s:], d["hit"][s:], d["obs_max_range"][s:])
+    assert [r1["updated_voxels"], r2["updated_voxels"]] == d["updated"].tolist()   # exact visit counts
+    occ = g.occ.cpu().numpy()
+    idx = keys - lo
+    np.testing.assert_allclose(occ[idx[:, 2], idx[:, 1], idx[:, 0]], probs, rtol=0, atol=1e-6)
+    touched = occ != np.float32(0.5)
+    assert int(touched.sum()) == len(keys)                        # exactly the reference's voxel set
+    assert int(g._counts.abs().sum().item()) == 0                  # scratch left zeroed
+    # scale: 200k rays from 8 sensors on a 256^3 grid, against the sequential oracle
+    rng = np.random.default_rng(3)
+    R = 200_000
+    sensors = rng.uniform(-10, 10, (8, 3))
+    pos = sensors[rng.integers(0, 8, R)]
+    dirs = rng.normal(0, 1, (R, 3))
+    hit = rng.uniform(0.5, 30.0, R)
+    hit[rng.random(R) < 0.25] = np.nan
+    g2 = dp.DenseOccupancyGrid((256, 256, 256), (-128, -128, -128), 0.2, max_range=25.0)
+    out = g2.update_map(pos, dirs, hit, 30.0)
+    og = oracle_mod.DenseGrid((256, 256, 256), (-128, -128, -128), 0.2)
+    occ64 = np.full(og.occ.shape, 0.5)
+    upd = oracle_mod.update_map(og, occ64, pos, dirs, hit, np.full(R, 30.0), 25.0)
+    assert out["updated_voxels"] == upd and out["observations_processed"] == R
+    got = g2.occ.cpu().numpy()
+    np.testing.assert_array_equal(got != np.float32(0.5), occ64 != 0.5)      # same voxels touched
+    np.testing.assert_allclose(got, occ64, rtol=0, atol=1e-6)

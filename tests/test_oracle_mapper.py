@@ -52,3 +52,24 @@ def test_bayes(oracle_mod):
         seq.append(p)
     np.testing.assert_allclose(seq, d["kat4"], atol=1e-15)
     np.testing.assert_allclose(seq[:3], [0.7, 0.844828, 0.890909], atol=1e-6)
+
+
+def test_oracle_update_map_matches_reference_fixture(oracle_mod):
+    """update_map (:100-152): two scans through the oracle vs the reference mapper's dict."""
+    d = load_golden("update_map")
+    keys, probs, counts = d["keys"], d["probs"], d["counts"]
+    lo = keys.min(0) - 1
+    shape = tuple(int(v) for v in (keys.max(0) - lo + 2))
+    g = oracle_mod.DenseGrid(shape, tuple(int(v) for v in lo), float(d["res"]))
+    occ = np.full(g.occ.shape, 0.5)
+    cnt = np.zeros(g.occ.shape, np.int32)
+    s = int(d["split"])
+    u1 = oracle_mod.update_map(g, occ, d["pos"][:s], d["dir"][:s], d["hit"][:s], d["obs_max_range"][:s],
+                               float(d["mapper_max_range"]), cnt)
+    u2 = oracle_mod.update_map(g, occ, d["pos"][s:], d["dir"][s:], d["hit"][s:], d["obs_max_range"][s:],
+                               float(d["mapper_max_range"]), cnt)
+    assert [u1, u2] == d["updated"].tolist()
+    idx = keys - lo
+    np.testing.assert_allclose(occ[idx[:, 2], idx[:, 1], idx[:, 0]], probs, rtol=0, atol=1e-15)
+    np.testing.assert_array_equal(cnt[idx[:, 2], idx[:, 1], idx[:, 0]], counts)
+    assert int((cnt > 0).sum()) == len(keys)                       # no other voxel was touched

@@ -279,7 +279,41 @@ def gen_mapper():
     save("mapper", d)
 
 
+def gen_update_map():
+    """update_map (explicit_geometric_mapper.py:100-152) on LiDAR-like scans: the resulting
+    sparse dict of occupancy probabilities (keys + values) and the returned counters."""
+    from dart_planner.perception.explicit_geometric_mapper import SensorObservation
+    rng = np.random.default_rng(11)
+    mp = ExplicitGeometricMapper(resolution=0.5, max_range=12.0)
+    R = 600
+    sensors = np.array([[0.2, 0.3, 1.0], [4.1, -2.2, 2.5], [-3.3, 3.7, 1.4]])
+    pos = sensors[rng.integers(0, 3, R)]
+    dirs = rng.normal(0, 1, (R, 3))
+    dirs[:30, 2] = 0.0                               # planar sweep
+    hit = rng.uniform(0.3, 15.0, R)                  # some beyond the mapper's max_range
+    hit[rng.random(R) < 0.3] = np.nan                # no return -> max_range, endpoint is a miss
+    hit[5] = 0.0                                     # falsy hit distance quirk (:112)
+    mr = np.full(R, 10.0)
+    mr[::7] = 20.0
+    obs = [SensorObservation(position=pos[i], direction=dirs[i],
+                             hit_distance=None if np.isnan(hit[i]) else float(hit[i]),
+                             max_range=float(mr[i]), timestamp=float(i)) for i in range(R)]
+    out = mp.update_map(obs[: R // 2])
+    out2 = mp.update_map(obs[R // 2:])               # second batch on top of the first
+    keys = np.array(sorted(mp.voxels), np.int32)
+    probs = np.array([mp.voxels[tuple(k)].occupancy_probability for k in keys])
+    counts = np.array([mp.voxels[tuple(k)].observation_count for k in keys], np.int32)
+    save("update_map", dict(res=np.float64(0.5), mapper_max_range=np.float64(12.0), pos=pos, dir=dirs,
+                            hit=hit, obs_max_range=mr, split=np.int32(R // 2), keys=keys, probs=probs,
+                            counts=counts, updated=np.array([out["updated_voxels"], out2["updated_voxels"]],
+                                                            np.int64)))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "update_map":
+        gen_update_map()
+        sys.exit(0)
     gen_solver()
     gen_extract()
     gen_mapper()
+    gen_update_map()

@@ -64,7 +64,7 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
         __syncwarp();
         const long long b = blk * GPB + gib;
         if (b >= A.B) continue;
-        Solver<SubWarp<LANES>, TPL, GM> sv(P, sm, ws, wy);
+        Solver<SubWarp<LANES>, TPL, GM, (MINB >= 3)> sv(P, sm, ws, wy);
         if (GM == 2) {
             sv.obs.g = A.grid;
             sv.obs.w = P.w_obstacle;

@@ -13,8 +13,18 @@ def _params(d):
     return make_params(cfg)
 
 
+@pytest.fixture(params=[0, 1], ids=["regs", "capped"])
+def policy(request):
+    """0: the register-rich build (line-search state and status words in registers);
+    1: the register-capped build's policies (shared line-search state, status bit sets)."""
+    import emu
+    emu.lib().emu_set_ls_shared(request.param)
+    yield request.param
+    emu.lib().emu_set_ls_shared(0)
+
+
 @pytest.mark.parametrize("name", SOLVER_FIXTURES)
-def test_core_matches_reference_fixture(name):
+def test_core_matches_reference_fixture(name, policy):
     import emu
     d = load_golden(name)
     xw = d["x_prev"] if "x_prev" in d.files else None
@@ -22,7 +32,7 @@ def test_core_matches_reference_fixture(name):
     assert_solution_parity(r, d, name)
 
 
-def test_core_matches_oracle_random(oracle_mod):
+def test_core_matches_oracle_random(oracle_mod, policy):
     import emu
     from dart_planner_b200.config import SE3MPCConfig, make_params
     rng = np.random.default_rng(99)

@@ -17,10 +17,14 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "--extended-lambda", "-Xcompiler", "
 # per-file extra flags; the mapper needs unfused multiply/add for bit-exact voxel indices
 UNITS = {
     "se3mpc_kernels.cu": [],
+    "se3mpc_inst_l4.cu": [], "se3mpc_inst_l8.cu": [], "se3mpc_inst_l16.cu": [],
+    "se3mpc_inst_l32.cu": [], "se3mpc_inst_l32x2.cu": [], "se3mpc_inst_l8_occ3.cu": [],
+    "se3mpc_inst_l8_b64.cu": [],
     "mapper_kernels.cu": ["-fmad=false"],
     "probe_kernels.cu": [],
 }
 HEADERS = [os.path.join(CSRC, "se3mpc_core.cuh"), os.path.join(CSRC, "map_query.cuh"),
+           os.path.join(CSRC, "se3mpc_kernel.cuh"),
            os.path.join(HERE, "..", "include", "dart_se3mpc.h")]
 
 

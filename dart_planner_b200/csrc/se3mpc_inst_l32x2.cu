@@ -1,0 +1,6 @@
+/* instantiation unit: solve kernels <LANES, TPL, MINB, BLOCK> = <32, 2, 2, 128> (see se3mpc_kernel.cuh) */
+#include "se3mpc_kernel.cuh"
+
+namespace dartb200 {
+KernelSet kernel_set_l32x2() { return make_kernel_set<32, 2, 2, 128>(); }
+}

@@ -1,10 +1,8 @@
 /*
- * se3mpc_kernels.cu -- sm_100a kernels + C ABI (include/dart_se3mpc.h) of the batched
- * SE(3)-MPC solve.  One problem per sub-warp (see se3mpc_core.cuh); a persistent grid walks
- * the batch with a grid-stride loop.  I/O is batch-major SoA so the 32/LANES problems of a
- * warp touch consecutive addresses of every row.
- *
- * Replaces: SE3MPCPlanner._solve_se3_mpc (se3_mpc_planner.py:230-280) for B problems.
+ * se3mpc_kernels.cu -- C ABI (include/dart_se3mpc.h) of the batched SE(3)-MPC solve: argument
+ * checks, kernel choice, launch.  The kernel itself is in se3mpc_kernel.cuh / se3mpc_core.cuh;
+ * its instantiations live in se3mpc_inst_*.cu.  I/O is batch-major SoA so the 32/LANES
+ * problems of a warp touch consecutive addresses of every row.
  */
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -14,8 +12,7 @@
 #include <atomic>
 #include <mutex>
 
-#include "map_query.cuh"
-#include "se3mpc_core.cuh"
+#include "se3mpc_kernel.cuh"
 
 using namespace dartb200;
 
@@ -24,160 +21,24 @@ namespace {
 std::atomic<long long> g_launches{0};
 thread_local char g_err[256] = "";
 
-struct SolveArgs {
-    long long B, ld;
-    const double *p0, *v0, *goal;
-    const unsigned char *has_goal;
-    const double *x_warm;
-    const unsigned char *warm_mask;
-    double *x_out, *cost;
-    int *nit, *nfev, *status, *task;
-    double *acc, *att, *rates, *thrust;
-    /* fused post-solve safety check (is_trajectory_safe on the solved positions); off when
-     * first_hit == nullptr */
-    dart_grid grid;
-    double margin, threshold;
-    int *first_hit;
-    /* fused plant step of the closed-loop simulation (off when p_next == nullptr): the state is
-     * advanced with the first control of the new solution; may alias p0 / v0 */
-    double *p_next, *v_next;
-    double plant_dt;
-};
-
-template <int LANES, int TPL, int BLOCK, int MINB, int GM>
-__global__ void __launch_bounds__(BLOCK, MINB)
-se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_constant__ SolveArgs A)
-{
-    extern __shared__ double smem_all[];
-    constexpr int GPB = BLOCK / LANES; /* problems (groups) per block */
-    const int gib = threadIdx.x / LANES;
-    double *sm = smem_all + gib * SM_DOUBLES;
-    const int N = P.horizon;
-    const long long stride = (long long)gridDim.x * GPB;
-    double ws[MMAX][9 * TPL], wy[MMAX][9 * TPL]; /* per-lane S / Y pairs (local memory, L1) */
-    /* block-uniform trip count + a warp barrier per round: the sub-warps of a warp start every
-     * problem together (a sub-warp that converged early waits instead of running ahead into
-     * different code) */
-    (void)stride;
-    const long long rounds = (A.B + GPB - 1) / GPB;
-    for (long long blk = blockIdx.x; blk < rounds; blk += gridDim.x) {
-        __syncwarp();
-        const long long b = blk * GPB + gib;
-        if (b >= A.B) continue;
-        Solver<SubWarp<LANES>, TPL, GM, (MINB >= 3)> sv(P, sm, ws, wy);
-        if (GM == 2) {
-            sv.obs.g = A.grid;
-            sv.obs.w = P.w_obstacle;
-            sv.obs.free_level = P.obstacle_free_level;
-        }
-        double p0[3], v0[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            p0[c] = __ldg(A.p0 + c * A.ld + b);
-            v0[c] = __ldg(A.v0 + c * A.ld + b);
-            sv.goal[c] = __ldg(A.goal + c * A.ld + b);
-        }
-        sv.has_goal = A.has_goal ? (A.has_goal[b] != 0) : true;
-        const bool warm = A.x_warm != nullptr && (A.warm_mask == nullptr || A.warm_mask[b] != 0);
-        if (warm) {
-            /* plain loads: in the closed loop x_out aliases x_warm */
-            const double *xw = A.x_warm + b;
-            const long long ld = A.ld;
-            sv.warm_start(p0, v0, [xw, ld](int row) { return xw[(long long)row * ld]; });
-        } else
-            sv.cold_start(p0, v0);
-        SolveStats st;
-        sv.minimize(st);
-        if (A.x_out) {
-#pragma unroll
-            for (int tt = 0; tt < TPL; ++tt)
-                if (sv.act[tt]) {
-#pragma unroll
-                    for (int q = 0; q < 9; ++q)
-                        A.x_out[(long long)sv.row_of(tt, q) * A.ld + b] = sv.x[tt * 9 + q];
-                }
-        }
-        if (sv.grp.leader()) {
-            if (A.cost) A.cost[b] = st.f;
-            if (A.nit) A.nit[b] = st.nit;
-            if (A.nfev) A.nfev[b] = st.nfev;
-            if (A.status) A.status[b] = st.status;
-            if (A.task) A.task[b] = st.task;
-        }
-        if (A.acc || A.att || A.rates || A.thrust) {
-            const SolveArgs &a = A;
-            sv.extract([&a, b](int k, double ax, double ay, double az, double r0, double r1,
-                               double r2, double w0, double w1, double w2, double th) {
-                const long long ld = a.ld;
-                if (a.acc) {
-                    a.acc[(long long)(3 * k) * ld + b] = ax;
-                    a.acc[(long long)(3 * k + 1) * ld + b] = ay;
-                    a.acc[(long long)(3 * k + 2) * ld + b] = az;
-                }
-                if (a.att) {
-                    a.att[(long long)(3 * k) * ld + b] = r0;
-                    a.att[(long long)(3 * k + 1) * ld + b] = r1;
-                    a.att[(long long)(3 * k + 2) * ld + b] = r2;
-                }
-                if (a.rates) {
-                    a.rates[(long long)(3 * k) * ld + b] = w0;
-                    a.rates[(long long)(3 * k + 1) * ld + b] = w1;
-                    a.rates[(long long)(3 * k + 2) * ld + b] = w2;
-                }
-                if (a.thrust) a.thrust[(long long)k * ld + b] = th;
-            });
-        }
-        if (A.first_hit) {
-            /* each lane tests its own timesteps against the map; the first colliding index is
-             * the minimum over the group (explicit_geometric_mapper.py:195-219) */
-            int hit = 0x7fffffff;
-#pragma unroll
-            for (int tt = TPL - 1; tt >= 0; --tt)
-                if (sv.act[tt] && position_collides(A.grid, sv.x[tt * 9], sv.x[tt * 9 + 1], sv.x[tt * 9 + 2],
-                                                    A.margin, A.threshold))
-                    hit = sv.grp.lane() * TPL + tt;
-            hit = sv.grp.mini(hit);
-            if (sv.grp.leader()) A.first_hit[b] = (hit == 0x7fffffff) ? -1 : hit;
-        }
-        if (A.p_next && sv.grp.leader()) {
-            /* reference planner model (se3_mpc_planner.py:430-431, :445-459) driven by T_0:
-             * a = T_0/m - g e3;  p <- p + v dt + (0.5 a) dt^2;  v <- v + a dt.  Every operation
-             * individually rounded (NumPy's order). */
-            const double dt = A.plant_dt, dt2 = DP_MUL(dt, dt);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const double a = DP_ADD(ddiv(sv.x[6 + c], P.mass), c == 2 ? -P.gravity : -0.0);
-                A.p_next[c * A.ld + b] = DP_ADD(DP_ADD(p0[c], DP_MUL(v0[c], dt)), DP_MUL(DP_MUL(0.5, a), dt2));
-                A.v_next[c * A.ld + b] = DP_ADD(v0[c], DP_MUL(a, dt));
-            }
-        }
-        (void)N;
-    }
-}
-
 struct KernelChoice {
-    const void *fn;       /* gradient_mode 0: the reference gradient (:552-580) */
-    const void *fn_exact; /* gradient_mode 1: exact gradient of :516-550       */
-    const void *fn_grid;  /* gradient_mode 2: mode 0 + occupancy-grid penalty  */
+    KernelSet set; /* fn[gradient_mode][tilt]; tilt = 0: launches without warm starts, whose lateral
+                    * thrust slots are exactly zero and stay zero -- 7 slots per timestep instead
+                    * of 9, bit-identical results */
     int lanes, tpl, block, minb;
     int occ_blocks; /* resident blocks per SM (queried once) */
     int regs;
     bool ready;
 };
 
-constexpr int BLOCK = 128;
-
-template <int LANES, int TPL, int MINB, int BLK = BLOCK>
-KernelChoice make_choice()
+KernelChoice make_choice(const KernelSet &ks)
 {
     KernelChoice k;
-    k.fn = (const void *)se3mpc_solve_kernel<LANES, TPL, BLK, MINB, 0>;
-    k.fn_exact = (const void *)se3mpc_solve_kernel<LANES, TPL, BLK, MINB, 1>;
-    k.fn_grid = (const void *)se3mpc_solve_kernel<LANES, TPL, BLK, MINB, 2>;
-    k.lanes = LANES;
-    k.tpl = TPL;
-    k.block = BLK;
-    k.minb = MINB;
+    k.set = ks;
+    k.lanes = ks.lanes;
+    k.tpl = ks.tpl;
+    k.block = ks.block;
+    k.minb = ks.minb;
     k.occ_blocks = 0;
     k.regs = 0;
     k.ready = false;
@@ -185,10 +46,11 @@ KernelChoice make_choice()
 }
 
 KernelChoice g_kernels[] = {
-    make_choice<4, 1, 2>(), make_choice<8, 1, 2>(), make_choice<16, 1, 2>(),
-    make_choice<32, 1, 2>(), make_choice<32, 2, 2>(),
-    /* tuning variants, selected with DART_SE3MPC_VARIANT=<index> (tools/kbench.py) */
-    make_choice<8, 1, 3>(), make_choice<8, 1, 4, 64>(),
+    make_choice(kernel_set_l4()), make_choice(kernel_set_l8()), make_choice(kernel_set_l16()),
+    make_choice(kernel_set_l32()), make_choice(kernel_set_l32x2()),
+    /* [5] the 168-register throughput build for N <= 8 (3 resident blocks per SM); [6] tuning
+     * variant (64-thread blocks), DART_SE3MPC_VARIANT=<index> (tools/kbench.py) */
+    make_choice(kernel_set_l8_occ3()), make_choice(kernel_set_l8_b64()),
 };
 std::mutex g_mu;
 int g_sms = 0;
@@ -231,7 +93,7 @@ int prepare(KernelChoice *k)
         if (e != cudaSuccess) return set_err(e, "cudaDeviceGetAttribute");
     }
     const int smem = smem_bytes(*k);
-    for (const void *fn : {k->fn, k->fn_exact, k->fn_grid}) {
+    for (const void *fn : {k->set.fn[0][0], k->set.fn[0][1], k->set.fn[1][0], k->set.fn[1][1], k->set.fn[2][0], k->set.fn[2][1]}) {
         e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return set_err(e, "cudaFuncSetAttribute(smem)");
     }
@@ -239,15 +101,15 @@ int prepare(KernelChoice *k)
      * the driver reserves); the rest stays L1 for the per-lane S/Y pairs in local memory */
     int carve = (int)((long long)k->minb * (smem + 1024) * 100 / (228 * 1024)) + 1;
     if (carve > 100) carve = 100;
-    for (const void *fn : {k->fn, k->fn_exact, k->fn_grid}) {
+    for (const void *fn : {k->set.fn[0][0], k->set.fn[0][1], k->set.fn[1][0], k->set.fn[1][1], k->set.fn[2][0], k->set.fn[2][1]}) {
         e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         if (e != cudaSuccess) return set_err(e, "cudaFuncSetAttribute(carveout)");
     }
     cudaFuncAttributes fa;
-    e = cudaFuncGetAttributes(&fa, k->fn);
+    e = cudaFuncGetAttributes(&fa, k->set.fn[0][1]);
     if (e != cudaSuccess) return set_err(e, "cudaFuncGetAttributes");
     k->regs = fa.numRegs;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k->occ_blocks, k->fn, k->block, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k->occ_blocks, k->set.fn[0][1], k->block, smem);
     if (e != cudaSuccess) return set_err(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
     if (k->occ_blocks < 1) k->occ_blocks = 1;
     k->ready = true;
@@ -337,7 +199,8 @@ static int launch_solve(const dart_se3mpc_params *params, const SolveArgs &a, vo
     SolveArgs args_copy = a;
     void *args[] = {(void *)&P, (void *)&args_copy};
     const long long grid_blocks = grid_for(*k, a.B);
-    const void *fn = params->gradient_mode == 1 ? k->fn_exact : (params->gradient_mode == 2 ? k->fn_grid : k->fn);
+    const int cold = (a.x_warm == nullptr && !getenv("DART_SE3MPC_NO_COLD")) ? 0 : 1;
+    const void *fn = k->set.fn[params->gradient_mode][cold];
     cudaError_t e = cudaLaunchKernel(fn, dim3((unsigned)grid_blocks), dim3(k->block), args,
                                      smem_bytes(*k), (cudaStream_t)cuda_stream);
     if (e != cudaSuccess) return set_err(e, "cudaLaunchKernel(se3mpc_solve)");

@@ -15,7 +15,10 @@ static int g_ls_shared = 0; /* 1: the register-capped build's policies (shared l
                              * state, status bit sets) */
 extern "C" void emu_set_ls_shared(int v) { g_ls_shared = v; }
 
-template <int TPL, int GM, bool LSS>
+static int g_cold_special = 0; /* 1: cold starts run the TILT=false instantiation */
+extern "C" void emu_set_cold_special(int v) { g_cold_special = v; }
+
+template <int TPL, int GM, bool LSS, bool TILT>
 static void solve_one(const dart_se3mpc_params &P, const double *p0, const double *v0,
                       const double *goal, int has_goal, const double *xw, double *x_out,
                       double *acc, double *att, double *rates, double *thrust, SolveStats &st,
@@ -24,7 +27,7 @@ static void solve_one(const dart_se3mpc_params &P, const double *p0, const doubl
     double smem[SM_DOUBLES];
     for (int i = 0; i < SM_DOUBLES; ++i) smem[i] = 0.0 / 0.0; /* NaN-poison: catches stale reads */
     static double ws[MMAX][9 * TPL], wy[MMAX][9 * TPL];
-    Solver<SeqGroup, TPL, GM, LSS> sv(P, smem, ws, wy);
+    Solver<SeqGroup, TPL, GM, LSS, TILT> sv(P, smem, ws, wy);
     const int N = P.horizon;
     if (GM == 2) {
         sv.obs.g = *grid;
@@ -62,8 +65,9 @@ extern "C" int emu_solve_batch(const dart_se3mpc_params *P, long B, const double
         SolveStats st;
         const double *xw = x_warm ? x_warm + (long)n * b : nullptr;
         const int hg = has_goal ? has_goal[b] : 1;
-#define CALL2(T, GM, L) solve_one<T, GM, L>(*P, p0 + 3 * b, v0 + 3 * b, goal + 3 * b, hg, xw, x + (long)n * b, \
+#define CALL3(T, GM, L, TI) solve_one<T, GM, L, TI>(*P, p0 + 3 * b, v0 + 3 * b, goal + 3 * b, hg, xw, x + (long)n * b, \
                              acc + 3L * N * b, att + 3L * N * b, rates + 3L * N * b, thrust + (long)N * b, st, grid)
+#define CALL2(T, GM, L) do { if (g_cold_special && !xw) CALL3(T, GM, L, false); else CALL3(T, GM, L, true); } while (0)
 #define CALL1(T, GM) do { if (g_ls_shared) CALL2(T, GM, true); else CALL2(T, GM, false); } while (0)
 #define CALL(T) do { if (P->gradient_mode == 1) CALL1(T, 1); else if (P->gradient_mode == 2) CALL1(T, 2); else CALL1(T, 0); } while (0)
         if (N <= 8) CALL(8);
@@ -72,6 +76,7 @@ extern "C" int emu_solve_batch(const dart_se3mpc_params *P, long B, const double
 #undef CALL
 #undef CALL1
 #undef CALL2
+#undef CALL3
         cost[b] = st.f; nit[b] = st.nit; nfev[b] = st.nfev; status[b] = st.status; task[b] = st.task;
     }
     return 0;

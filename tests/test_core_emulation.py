@@ -13,14 +13,17 @@ def _params(d):
     return make_params(cfg)
 
 
-@pytest.fixture(params=[0, 1], ids=["regs", "capped"])
+@pytest.fixture(params=[0, 1, 2], ids=["regs", "capped", "cold7"])
 def policy(request):
     """0: the register-rich build (line-search state and status words in registers);
-    1: the register-capped build's policies (shared line-search state, status bit sets)."""
+    1: the register-capped build's policies (shared line-search state, status bit sets);
+    2: cold starts through the 7-slot instantiation (lateral thrust slots skipped)."""
     import emu
-    emu.lib().emu_set_ls_shared(request.param)
+    emu.lib().emu_set_ls_shared(1 if request.param == 1 else 0)
+    emu.lib().emu_set_cold_special(1 if request.param == 2 else 0)
     yield request.param
     emu.lib().emu_set_ls_shared(0)
+    emu.lib().emu_set_cold_special(0)
 
 
 @pytest.mark.parametrize("name", SOLVER_FIXTURES)

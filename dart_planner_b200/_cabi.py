@@ -55,7 +55,7 @@ EXPORTS = [
     "dart_se3mpc_solve_batch_host",
     "dart_launch_count",
     "dart_se3mpc_kernel_info", "dart_map_query_batch", "dart_map_traj_safe_batch",
-    "dart_map_trace_ray_batch", "dart_map_update_batch", "dart_map_add_spheres", "dart_fp64_probe",
+    "dart_map_trace_ray_batch", "dart_map_update_batch", "dart_map_add_spheres", "dart_fp64_probe", "dart_ddiv_selftest",
 ]
 
 _lib = None
@@ -107,6 +107,8 @@ def lib():
     L.dart_map_add_spheres.restype = C.c_int
     L.dart_fp64_probe.argtypes = [i32, C.POINTER(i32), vp, vp]
     L.dart_fp64_probe.restype = C.c_int
+    L.dart_ddiv_selftest.argtypes = [i64, C.c_uint64, i32, vp, vp]
+    L.dart_ddiv_selftest.restype = C.c_int
     if L.dart_abi_version() != 1:
         raise RuntimeError("libdart_se3mpc.so ABI version mismatch")
     _lib = L

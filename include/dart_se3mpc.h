@@ -69,6 +69,13 @@ typedef struct dart_se3mpc_params {
     double w_obstacle, obstacle_free_level;
 } dart_se3mpc_params;
 
+/* Self-test of the solver's in-line fp64 division (reciprocal seed + Newton + residual
+ * correction, csrc/se3mpc_core.cuh) against IEEE division on n random operand pairs with
+ * magnitudes in 2^[-emax, emax]; *mismatch_dev (device uint64, caller-zeroed) += number of
+ * quotients whose bits differ. */
+int dart_ddiv_selftest(int64_t n, uint64_t seed, int32_t emax, uint64_t *mismatch_dev,
+                       void *cuda_stream);
+
 /* ---- occupancy grid (perception/explicit_geometric_mapper.py) on a dense device grid ----
  * occ: float32 [nz][ny][nx] (x fastest); voxel key (kx,ky,kz) = floor(p/res) lives at index
  * (kx-ox, ky-oy, kz-oz); keys outside the grid read `prior` (the reference's dict miss, :168). */

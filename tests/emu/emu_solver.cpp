@@ -67,15 +67,18 @@ extern "C" int emu_solve_batch(const dart_se3mpc_params *P, long B, const double
         const int hg = has_goal ? has_goal[b] : 1;
 #define CALL3(T, GM, L, TI) solve_one<T, GM, L, TI>(*P, p0 + 3 * b, v0 + 3 * b, goal + 3 * b, hg, xw, x + (long)n * b, \
                              acc + 3L * N * b, att + 3L * N * b, rates + 3L * N * b, thrust + (long)N * b, st, grid)
-#define CALL2(T, GM, L) do { if (g_cold_special && !xw) CALL3(T, GM, L, false); else CALL3(T, GM, L, true); } while (0)
-#define CALL1(T, GM) do { if (g_ls_shared) CALL2(T, GM, true); else CALL2(T, GM, false); } while (0)
-#define CALL(T) do { if (P->gradient_mode == 1) CALL1(T, 1); else if (P->gradient_mode == 2) CALL1(T, 2); else CALL1(T, 0); } while (0)
-        if (N <= 8) CALL(8);
-        else if (N <= 20) CALL(20);
-        else CALL(32);
+/* the build policies (throughput build, 7-slot cold start) are emulated at the N <= 8 size only */
+#define CALLP(T, GM) do { \
+        if (g_cold_special && !xw) { if (g_ls_shared) CALL3(T, GM, true, false); else CALL3(T, GM, false, false); } \
+        else { if (g_ls_shared) CALL3(T, GM, true, true); else CALL3(T, GM, false, true); } } while (0)
+#define CALLG(T, GM) CALL3(T, GM, false, true)
+#define CALL(T, F) do { if (P->gradient_mode == 1) F(T, 1); else if (P->gradient_mode == 2) F(T, 2); else F(T, 0); } while (0)
+        if (N <= 8) CALL(8, CALLP);
+        else if (N <= 20) CALL(20, CALLG);
+        else CALL(32, CALLG);
 #undef CALL
-#undef CALL1
-#undef CALL2
+#undef CALLG
+#undef CALLP
 #undef CALL3
         cost[b] = st.f; nit[b] = st.nit; nfev[b] = st.nfev; status[b] = st.status; task[b] = st.task;
     }

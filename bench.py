@@ -63,6 +63,18 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def bind_to_gpu_numa(index):
+    """Pin this rank to the CPUs NVML reports as local to its GPU, before any pinned buffer is
+    allocated, so the end-to-end copies of the N ranks do not cross sockets."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+        return True
+    except Exception:
+        return False
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons through NVML while the timed regions run."""
 
@@ -203,6 +215,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    all_cpus = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    numa_bound = bind_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -293,6 +307,7 @@ def main():
                 "api": "dart_planner_b200.planner.BatchWorkspace.solve_staged (pinned host buffers)"},
         "gpu_launches": int(launches),
         "roofline": roofline,
+        "host": {"numa_bound_to_gpu": bool(numa_bound), "cores_visible": len(all_cpus) if all_cpus else None},
     }
     info = [C.c_int32() for _ in range(5)]
     if L.dart_se3mpc_kernel_info(C.byref(params), B, *[C.byref(i) for i in info]) == 0:
@@ -317,6 +332,8 @@ def main():
         fp64_peak = th.value * 8.0 * iters * 2.0 / (a.elapsed_time(b) * 1e-3) / 1e12
         # CPU baseline + algorithmic flops from the instrumented oracle on the same batch
         import oracle
+        if all_cpus is not None:
+            os.sched_setaffinity(0, all_cpus)     # the CPU baseline uses every host core again
         cores = host_cores()
         oparams = oracle.make_params(horizon=N, dt=args.dt)
         r1 = oracle.solve_batch(oparams, p0, v0, goal, nthreads=cores)
@@ -416,6 +433,16 @@ def main():
         lat = lat[60:]
         line["single_solve_latency_ms"] = {"p50": statistics.median(lat), "p95": sorted(lat)[int(0.95 * len(lat))],
                                            "api": "SE3MPCPlanner.plan (host in, host out)", "n": len(lat)}
+        # the same single problem on one host core through the CPU port (reported beside it: a GPU
+        # does not win single-problem latency against a C port; the reference's own Python path
+        # is 2.1 ms)
+        p1 = np.array([[0.0, 0.0, 2.0]]); g1 = np.array([[10.0, 0.0, 5.0]])
+        clat = []
+        for i in range(260):
+            t0 = time.perf_counter()
+            oracle.solve_batch(oparams, p1, np.zeros((1, 3)), g1, nthreads=1)
+            clat.append((time.perf_counter() - t0) * 1e3)
+        line["single_solve_latency_ms"]["cpu_port_p50"] = statistics.median(clat[60:])
     sampler.stop()
     line["clocks"] = sampler.summary()
     print(json.dumps(line), flush=True)

@@ -49,6 +49,10 @@ class ClosedLoopSim:
         self.meta = torch.zeros((3, self.ld), dtype=torch.int32, device=self.device)  # nit, nfev, status
         self.nfev_total = torch.zeros(self.ld, dtype=torch.int64, device=self.device)
         self.steps_done = 0
+        # the solutions held in self.x come from cold starts of this solver, so their lateral
+        # thrust is exactly zero and stays zero: warm starts may use the 7-slot kernel (warm=2;
+        # the kernel verifies).  Anyone writing self.x by hand must clear this flag.
+        self.lateral_thrust_is_zero = True
         self._lib = _cabi.lib()
 
     def reset(self, p0, v0, goals):
@@ -60,6 +64,7 @@ class ClosedLoopSim:
         self.x.zero_()
         self.nfev_total.zero_()
         self.steps_done = 0
+        self.lateral_thrust_is_zero = True
 
     def step(self, stream=None, track_counters: bool = True):
         """One replanning step (one launch): solve, store the solution, advance the plant."""
@@ -70,7 +75,8 @@ class ClosedLoopSim:
         with torch.cuda.device(self.device):
             rc = self._lib.dart_se3mpc_closed_loop_step(
                 C.byref(self.params), self.B, self.ld, base, base + 3 * es, base + 6 * es, None,
-                self.x.data_ptr(), 1 if self.steps_done > 0 else 0, self.cost.data_ptr(),
+                self.x.data_ptr(),
+                0 if self.steps_done == 0 else (2 if self.lateral_thrust_is_zero else 1), self.cost.data_ptr(),
                 self.meta.data_ptr(), self.meta.data_ptr() + 4 * self.ld, self.meta.data_ptr() + 8 * self.ld,
                 self.plant_dt, stream.cuda_stream)
         _cabi.check(rc, "dart_se3mpc_closed_loop_step")

@@ -31,6 +31,10 @@ struct SolveArgs {
      * advanced with the first control of the new solution; may alias p0 / v0 */
     double *p_next, *v_next;
     double plant_dt;
+    /* the caller promises that every lateral thrust entry of x_warm is exactly zero (solutions
+     * this library produced from cold starts): the 7-slot instantiation then serves warm starts
+     * too.  The kernel checks the promise per problem and refuses (status 3) where it is broken. */
+    int no_tilt_promise;
 };
 
 template <int LANES, int TPL, int BLOCK, int MINB, int GM, bool TILT>
@@ -73,6 +77,21 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
             const double *xw = A.x_warm + b;
             const long long ld = A.ld;
             sv.warm_start(p0, v0, [xw, ld](int row) { return xw[(long long)row * ld]; });
+            if (!TILT) {
+                int tilted = 0;
+#pragma unroll
+                for (int tt = 0; tt < TPL; ++tt)
+                    tilted |= (sv.x[tt * 9 + 6] != 0.0 || sv.x[tt * 9 + 7] != 0.0) ? 1 : 0;
+                if (sv.grp.ori(tilted)) { /* broken promise: no solve, say so */
+                    if (sv.grp.leader()) {
+                        if (A.status) A.status[b] = 3;
+                        if (A.nit) A.nit[b] = 0;
+                        if (A.nfev) A.nfev[b] = 0;
+                        if (A.cost) A.cost[b] = nan("");
+                    }
+                    continue;
+                }
+            }
         } else
             sv.cold_start(p0, v0);
         SolveStats st;

@@ -199,7 +199,7 @@ static int launch_solve(const dart_se3mpc_params *params, const SolveArgs &a, vo
     SolveArgs args_copy = a;
     void *args[] = {(void *)&P, (void *)&args_copy};
     const long long grid_blocks = grid_for(*k, a.B);
-    const int cold = (a.x_warm == nullptr && !getenv("DART_SE3MPC_NO_COLD")) ? 0 : 1;
+    const int cold = ((a.x_warm == nullptr || a.no_tilt_promise) && !getenv("DART_SE3MPC_NO_COLD")) ? 0 : 1;
     const void *fn = k->set.fn[params->gradient_mode][cold];
     cudaError_t e = cudaLaunchKernel(fn, dim3((unsigned)grid_blocks), dim3(k->block), args,
                                      smem_bytes(*k), (cudaStream_t)cuda_stream);
@@ -256,6 +256,7 @@ int dart_se3mpc_closed_loop_step(const dart_se3mpc_params *params, int64_t B, in
     a.B = B; a.ld = ld;
     a.p0 = p; a.v0 = v; a.goal = goal; a.has_goal = has_goal;
     a.x_warm = warm ? x : nullptr;
+    a.no_tilt_promise = (warm == 2) ? 1 : 0;
     a.x_out = x; a.cost = cost; a.nit = nit; a.nfev = nfev; a.status = status;
     a.p_next = p; a.v_next = v; a.plant_dt = plant_dt;
     return launch_solve(params, a, cuda_stream);

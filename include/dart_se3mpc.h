@@ -138,7 +138,11 @@ int dart_se3mpc_solve_batch_map(const dart_se3mpc_params *params, int64_t B, int
  * write the new solution to x, then advance the state in place with the planner's own model
  * (:430-431, :445-459) driven by the first control:  a = T_0/m - g e3,
  * p <- p + v*dt + 0.5*a*dt^2,  v <- v + a*dt  (dt = plant_dt).
- * p, v : [3][ld] in/out;  x : [9N][ld] in/out;  cost/nit/nfev/status may be NULL. */
+ * p, v : [3][ld] in/out;  x : [9N][ld] in/out;  cost/nit/nfev/status may be NULL.
+ * warm == 2: warm start with the caller's promise that every lateral thrust entry (T_x, T_y) of
+ * x is exactly zero -- true for solutions this library produced from cold starts, since a zero
+ * lateral thrust has a zero gradient and never moves.  The faster 7-slot kernel then serves the
+ * warm start; a problem whose x breaks the promise is not solved and gets status 3. */
 int dart_se3mpc_closed_loop_step(const dart_se3mpc_params *params, int64_t B, int64_t ld, double *p,
                                  double *v, const double *goal, const uint8_t *has_goal, double *x,
                                  int32_t warm, double *cost, int32_t *nit, int32_t *nfev,

@@ -83,3 +83,34 @@ def test_closed_loop_first_step_is_the_plain_solve_plus_plant():
     warm = dp.plan_batch(p1, v1, goal, cfg, x_warm=sol.x, to_host=True)
     sim.step()
     np.testing.assert_array_equal(sim.solution().cpu().numpy(), warm.x)
+
+
+def test_closed_loop_seven_slot_warm_path_is_identical_and_checked():
+    """Warm starts whose lateral thrust is exactly zero run on the 7-slot kernel (warm=2): same
+    bits as the general warm kernel; a problem that breaks the promise is refused (status 3)."""
+    import dart_planner_b200 as dp
+    from dart_planner_b200.closed_loop import ClosedLoopSim
+    from dart_planner_b200.config import make_params
+    B, N, dt = 3000, 8, 0.1
+    p0, v0, goal = _inputs(17, B)
+    params = make_params(dp.SE3MPCConfig(prediction_horizon=N, dt=dt))
+    fast, gen = ClosedLoopSim(params, B, plant_dt=dt), ClosedLoopSim(params, B, plant_dt=dt)
+    fast.reset(p0, v0, goal)
+    gen.reset(p0, v0, goal)
+    gen.lateral_thrust_is_zero = False           # general 9-slot warm kernel
+    for s in range(12):
+        fast.step()
+        gen.step()
+        gen.lateral_thrust_is_zero = False
+    np.testing.assert_array_equal(fast.solution().cpu().numpy(), gen.solution().cpu().numpy())
+    np.testing.assert_array_equal(fast.positions().cpu().numpy(), gen.positions().cpu().numpy())
+    np.testing.assert_array_equal(fast.nfev_total.cpu().numpy(), gen.nfev_total.cpu().numpy())
+    # break the promise for a few problems: tilt their stored thrust
+    bad = [5, 77, 2999]
+    before = fast.positions().cpu().numpy().copy()
+    fast.x[6 * N + 3, bad] = 0.25                 # T_x of timestep 1
+    fast.step()
+    status = fast.meta[2, :B].cpu().numpy()
+    assert (status[bad] == 3).all() and (np.delete(status, bad) != 3).all()
+    assert np.isnan(fast.cost[:B].cpu().numpy()[bad]).all()
+    np.testing.assert_array_equal(fast.positions().cpu().numpy()[bad], before[bad])   # state untouched

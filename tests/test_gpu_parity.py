@@ -257,3 +257,43 @@ def test_inline_division_is_ieee_exact():
         rc = L.dart_ddiv_selftest(n, 12345 + emax, emax, bad.data_ptr(), torch.cuda.current_stream().cuda_stream)
         assert rc == 0
         assert int(bad.item()) == 0, f"{int(bad.item())} of {n} quotients differ from IEEE division (emax {emax})"
+
+
+@pytest.mark.parametrize("N,m,gm,maxiter", [(1, 10, 0, 15), (2, 10, 0, 15), (64, 10, 0, 15), (8, 3, 1, 40),
+                                            (8, 1, 1, 30), (6, 5, 1, 25), (33, 4, 1, 20)])
+def test_gpu_edge_configurations(oracle_mod, N, m, gm, maxiter):
+    """Horizon 1 (alpha = i/max(N-1,1)), the largest supported horizon (64: 32 lanes x 2 timesteps),
+    and small correction memories with the exact gradient, so the ring of pairs wraps many times."""
+    import dart_planner_b200 as dp
+    from dart_planner_b200.config import make_params
+    from dart_planner_b200.planner import BatchWorkspace
+    B = 512
+    p0, v0, goal = bench_inputs(100 + N + m, B, 1.5)
+    tol = 5e-2 if gm == 0 else 1e-7
+    cfg = dp.SE3MPCConfig(prediction_horizon=N, dt=0.1, max_iterations=maxiter, convergence_tolerance=tol)
+    op = oracle_mod.make_params(horizon=N, dt=0.1, max_iterations=maxiter, convergence_tolerance=tol,
+                                consistent_gradient=gm)
+    op.max_corrections = m
+    ref = oracle_mod.solve_batch(op, p0, v0, goal, nthreads=16)
+    ws = BatchWorkspace(make_params(cfg, gradient_mode=gm, max_corrections=m), B, pinned=False)
+    ws.set_inputs_device(p0, v0, goal)
+    sol = ws.solve_device().numpy()
+    if gm == 1:
+        assert ref.nit.max() > m            # the ring wrapped
+    _compare(sol, ref, min_counter_agreement=0.98 if gm == 1 else 1.0)
+
+
+def test_gpu_empty_and_no_goal_batches():
+    import dart_planner_b200 as dp
+    from dart_planner_b200.config import make_params
+    from dart_planner_b200.planner import solve_batch_tensors
+    import torch
+    cfg = dp.SE3MPCConfig(prediction_horizon=8, dt=0.1)
+    inp = torch.zeros((9, 32), dtype=torch.float64, device="cuda")
+    sol = solve_batch_tensors(make_params(cfg), inp, 0)                   # B = 0: no launch, no error
+    assert sol.B == 0 and sol.x.shape[0] == 0
+    p0, v0, goal = bench_inputs(3, 64, 1.0)
+    none = dp.plan_batch(p0, v0, goal, cfg, has_goal=np.zeros(64, np.uint8), to_host=True)
+    # without a goal the position terms vanish: positions stay at p0, the solve still runs
+    np.testing.assert_allclose(none.positions, np.repeat(p0[:, None, :], 8, axis=1), atol=0)
+    assert (none.nit >= 1).all()

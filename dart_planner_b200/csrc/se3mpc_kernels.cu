@@ -63,8 +63,12 @@ int set_err(cudaError_t e, const char *what)
     return DART_E_CUDA;
 }
 
+thread_local long long g_batch_hint = 0; /* > 0: choose the build for this many problems (the
+                                          * chunks of one pipelined host batch use one build) */
+
 KernelChoice *pick_kernel(int N, long long B)
 {
+    if (g_batch_hint > B) B = g_batch_hint;
     int idx = N <= 4 ? 0 : N <= 8 ? 1 : N <= 16 ? 2 : N <= 32 ? 3 : 4;
     /* N <= 8, many rounds of work: the 168-register build (3 resident blocks per SM) trades a
      * few spills for 50 % more warps in flight: +15 % at 64 Ki and 1 Mi problems, but -12 % on a
@@ -282,6 +286,7 @@ struct HostWs {
     void *pin = nullptr; /* pinned host mirror of the workspace (small batches) */
     size_t pin_cap = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr; /* second lane of the chunk pipeline (large batches) */
 };
 thread_local HostWs g_ws;
 
@@ -362,6 +367,68 @@ int dart_se3mpc_solve_batch_host(const dart_se3mpc_params *params, int64_t B,
             *d_task = d_status + Bp;
     uint8_t *d_hg = (uint8_t *)(base + L.hg_off);
     const size_t in_bytes = (x_warm ? L.in_rows : 9) * Bp * 8;
+    if (!staged && B >= 65536) {
+        /* Large batch: chunks of 32768 problems alternate between two streams, each doing its own
+         * pitched H2D rows -> solve -> pitched D2H rows, so the read-back of chunk i (the
+         * dominant cost: 1.3 KB per solve over PCIe) overlaps the solve of chunk i+1 and the
+         * upload of chunk i+2.  Fully asynchronous when the caller's buffers are pinned. */
+        if (!g_ws.stream2) {
+            e = cudaStreamCreateWithFlags(&g_ws.stream2, cudaStreamNonBlocking);
+            if (e != cudaSuccess) return set_err(e, "cudaStreamCreate");
+        }
+        const int64_t chunk = 32768;
+        int ci = 0;
+        struct HintScope { /* every chunk runs the build chosen for the whole batch */
+            explicit HintScope(long long b) { g_batch_hint = b; }
+            ~HintScope() { g_batch_hint = 0; }
+        } hint_scope(B);
+        for (int64_t c0 = 0; c0 < B; c0 += chunk, ++ci) {
+            const int64_t cb = (B - c0 < chunk) ? (B - c0) : chunk;
+            cudaStream_t cs = (ci & 1) ? g_ws.stream2 : g_ws.stream;
+#define ROWS_H2D(dst, src, rows, esz)                                                                        \
+    do {                                                                                                     \
+        e = cudaMemcpy2DAsync((char *)(dst) + c0 * (esz), Bp * (esz), (const char *)(src) + c0 * (esz),        \
+                              (size_t)B * (esz), (size_t)cb * (esz), rows, cudaMemcpyHostToDevice, cs);       \
+        if (e != cudaSuccess) return set_err(e, "cudaMemcpy2DAsync H2D");                                    \
+    } while (0)
+#define ROWS_D2H(dst, src, rows, esz)                                                                        \
+    do {                                                                                                     \
+        if (dst) {                                                                                           \
+            e = cudaMemcpy2DAsync((char *)(dst) + c0 * (esz), (size_t)B * (esz), (const char *)(src) + c0 * (esz), \
+                                  Bp * (esz), (size_t)cb * (esz), rows, cudaMemcpyDeviceToHost, cs);          \
+            if (e != cudaSuccess) return set_err(e, "cudaMemcpy2DAsync D2H");                                \
+        }                                                                                                    \
+    } while (0)
+            ROWS_H2D(d_p0, p0, 3, 8);
+            ROWS_H2D(d_v0, v0, 3, 8);
+            ROWS_H2D(d_goal, goal, 3, 8);
+            if (has_goal) ROWS_H2D(d_hg, has_goal, 1, 1);
+            if (x_warm) ROWS_H2D(d_xw, x_warm, 9 * N, 8);
+            rc = dart_se3mpc_solve_batch(params, cb, (int64_t)Bp, d_p0 + c0, d_v0 + c0, d_goal + c0,
+                                         has_goal ? d_hg + c0 : nullptr, x_warm ? d_xw + c0 : nullptr, nullptr,
+                                         x_out ? d_x + c0 : nullptr, cost ? d_cost + c0 : nullptr,
+                                         nit ? d_nit + c0 : nullptr, nfev ? d_nfev + c0 : nullptr,
+                                         status ? d_status + c0 : nullptr, nullptr, acc ? d_acc + c0 : nullptr,
+                                         att ? d_att + c0 : nullptr, rates ? d_rates + c0 : nullptr,
+                                         thrust ? d_thr + c0 : nullptr, (void *)cs);
+            if (rc) return rc;
+            ROWS_D2H(x_out, d_x, 9 * N, 8);
+            ROWS_D2H(cost, d_cost, 1, 8);
+            ROWS_D2H(nit, d_nit, 1, 4);
+            ROWS_D2H(nfev, d_nfev, 1, 4);
+            ROWS_D2H(status, d_status, 1, 4);
+            ROWS_D2H(acc, d_acc, 3 * N, 8);
+            ROWS_D2H(att, d_att, 3 * N, 8);
+            ROWS_D2H(rates, d_rates, 3 * N, 8);
+            ROWS_D2H(thrust, d_thr, N, 8);
+#undef ROWS_H2D
+#undef ROWS_D2H
+        }
+        e = cudaStreamSynchronize(g_ws.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g_ws.stream2);
+        if (e != cudaSuccess) return set_err(e, "cudaStreamSynchronize");
+        return DART_OK;
+    }
     if (staged) {
         char *h = (char *)g_ws.pin;
         rows_in(h, Bp, p0, (size_t)B, 3, 8);

@@ -343,6 +343,9 @@ class BatchWorkspace:
     def solve_staged(self, stream=None):
         """pinned H2D -> solve -> pinned D2H, all on one stream; returns after synchronising."""
         torch = _torch()
+        if (self.B >= 65536 and self.B == self.ld and self.has_goal is None and self.x_warm is None
+                and self.grid is None):
+            return self._solve_staged_pipelined()
         stream = stream or torch.cuda.current_stream(self.device)
         with torch.cuda.stream(stream):
             self.inp.copy_(self.h_inp, non_blocking=True)
@@ -351,6 +354,21 @@ class BatchWorkspace:
             self.h_out[:nrows].copy_(self.out[:nrows], non_blocking=True)
             self.h_meta.copy_(self.meta, non_blocking=True)
         stream.synchronize()
+        return self.h_out, self.h_meta
+
+    def _solve_staged_pipelined(self):
+        """Large batches: the C host entry splits the batch into chunks on two streams so the
+        read-back of one chunk overlaps the solve of the next (pinned buffers: fully async)."""
+        N, es = self.N, 8 * self.ld
+        hi, ho, hm = self.h_inp.data_ptr(), self.h_out.data_ptr(), self.h_meta.data_ptr()
+        derived = self.outputs == "all"
+        with _torch().cuda.device(self.device):
+            rc = _cabi.lib().dart_se3mpc_solve_batch_host(
+                C.byref(self.params), self.B, hi, hi + 3 * es, hi + 6 * es, None, None,
+                ho, ho + 9 * N * es, hm, hm + 4 * self.ld, hm + 8 * self.ld,
+                ho + (9 * N + 1) * es if derived else None, ho + (12 * N + 1) * es if derived else None,
+                ho + (15 * N + 1) * es if derived else None, ho + (18 * N + 1) * es if derived else None)
+        _cabi.check(rc, "dart_se3mpc_solve_batch_host")
         return self.h_out, self.h_meta
 
     def solve_host(self, p0, v0, goal) -> HostSolution:

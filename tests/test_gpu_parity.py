@@ -297,3 +297,25 @@ def test_gpu_empty_and_no_goal_batches():
     # without a goal the position terms vanish: positions stay at p0, the solve still runs
     np.testing.assert_allclose(none.positions, np.repeat(p0[:, None, :], 8, axis=1), atol=0)
     assert (none.nit >= 1).all()
+
+
+def test_pipelined_host_path_matches_device_path():
+    """>= 65536 problems from host buffers go through the chunked two-stream pipeline (pitched
+    H2D / solve / pitched D2H per 32768-problem chunk): same bits as the resident solve."""
+    import dart_planner_b200 as dp
+    from dart_planner_b200.config import make_params
+    from dart_planner_b200.planner import BatchWorkspace, HostSolution
+    B, N = 65536 + 32768 + 4096, 8          # three chunks, the last one partial
+    p0, v0, goal = bench_inputs(71, B, 1.0)
+    ws = BatchWorkspace(make_params(dp.SE3MPCConfig(prediction_horizon=N, dt=0.1)), B, pinned=True)
+    assert ws.B == ws.ld
+    ws.set_inputs_device(p0, v0, goal)
+    ref = ws.solve_device().numpy()
+    ws.out.zero_()
+    host = ws.solve_host(p0, v0, goal)
+    np.testing.assert_array_equal(host.x, ref.x)
+    np.testing.assert_array_equal(host.cost, ref.cost)
+    np.testing.assert_array_equal(host.nfev, ref.nfev)
+    np.testing.assert_array_equal(host.status, ref.status)
+    np.testing.assert_array_equal(host.body_rates, ref.body_rates)
+    np.testing.assert_array_equal(host.thrusts, ref.thrusts)

@@ -319,3 +319,27 @@ def test_pipelined_host_path_matches_device_path():
     np.testing.assert_array_equal(host.status, ref.status)
     np.testing.assert_array_equal(host.body_rates, ref.body_rates)
     np.testing.assert_array_equal(host.thrusts, ref.thrusts)
+
+
+def test_gpu_build_variants_agree(oracle_mod, monkeypatch):
+    """The latency build, the 168-register throughput build, the 64-thread-block build and the
+    general 9-slot instantiation (DART_SE3MPC_NO_COLD) solve the same batch to the same answer
+    (separate compilations may contract differently: agreement to 1e-11, identical counters)."""
+    import dart_planner_b200 as dp
+    p0, v0, goal = bench_inputs(55, 4096, 1.0)
+    cfg = dp.SE3MPCConfig(prediction_horizon=8, dt=0.1)
+    monkeypatch.delenv("DART_SE3MPC_VARIANT", raising=False)
+    base = dp.plan_batch(p0, v0, goal, cfg, to_host=True)
+    ref = oracle_mod.solve_batch(oracle_mod.make_params(horizon=8, dt=0.1), p0, v0, goal, nthreads=16)
+    _compare(base, ref)
+    for env in ({"DART_SE3MPC_VARIANT": "5"}, {"DART_SE3MPC_VARIANT": "6"}, {"DART_SE3MPC_NO_COLD": "1"},
+                {"DART_SE3MPC_VARIANT": "5", "DART_SE3MPC_NO_COLD": "1"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        got = dp.plan_batch(p0, v0, goal, cfg, to_host=True)
+        for k in env:
+            monkeypatch.delenv(k)
+        np.testing.assert_allclose(got.x, base.x, rtol=0, atol=1e-11, err_msg=str(env))
+        np.testing.assert_array_equal(got.nfev, base.nfev)
+        np.testing.assert_array_equal(got.status, base.status)
+        np.testing.assert_allclose(got.body_rates, base.body_rates, rtol=0, atol=1e-9)

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Small mixed workload for compute-sanitizer (memcheck / racecheck): cold + warm solves at several
+"""Small mixed workload touching every kernel and mode once (handy under a debugger or a memory
+checker where one is available): cold + warm solves at several
 horizons, the fused map check, the penalty mode, a closed-loop step and the mapper kernels."""
 import os
 import sys
@@ -31,4 +32,4 @@ sim.run(3)
 grid.update_map(rng.uniform(-5, 5, (200, 3)), rng.normal(0, 1, (200, 3)), rng.uniform(0.5, 20, 200), 10.0)
 grid.trace_rays(rng.uniform(-5, 5, (50, 3)), rng.normal(0, 1, (50, 3)), rng.uniform(0.5, 10, 50), max_vox=64)
 torch.cuda.synchronize()
-print("sanitize_case done")
+print("mixed_case done")

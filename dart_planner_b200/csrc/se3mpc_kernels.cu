@@ -28,7 +28,7 @@ struct KernelChoice {
     int lanes, tpl, block, minb;
     int occ_blocks; /* resident blocks per SM (queried once) */
     int regs;
-    bool ready;
+    unsigned long long ready; /* bit d: function attributes set on device d (they are per device) */
 };
 
 KernelChoice make_choice(const KernelSet &ks)
@@ -41,7 +41,7 @@ KernelChoice make_choice(const KernelSet &ks)
     k.minb = ks.minb;
     k.occ_blocks = 0;
     k.regs = 0;
-    k.ready = false;
+    k.ready = 0ull;
     return k;
 }
 
@@ -85,13 +85,14 @@ KernelChoice *pick_kernel(int N, long long B)
 int prepare(KernelChoice *k)
 {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (k->ready) return DART_OK;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) {
         set_err(e, "cudaGetDevice");
         return DART_E_NODEVICE;
     }
+    if (dev < 0 || dev >= 64) return DART_E_UNSUPPORTED;
+    if (k->ready >> dev & 1ull) return DART_OK;
     if (g_sms == 0) {
         e = cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return set_err(e, "cudaDeviceGetAttribute");
@@ -116,7 +117,7 @@ int prepare(KernelChoice *k)
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k->occ_blocks, k->set.fn[0][1], k->block, smem);
     if (e != cudaSuccess) return set_err(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
     if (k->occ_blocks < 1) k->occ_blocks = 1;
-    k->ready = true;
+    k->ready |= 1ull << dev;
     return DART_OK;
 }
 
@@ -287,6 +288,7 @@ struct HostWs {
     size_t pin_cap = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr; /* second lane of the chunk pipeline (large batches) */
+    int device = -1;                /* the device everything above belongs to */
 };
 thread_local HostWs g_ws;
 
@@ -336,6 +338,27 @@ int dart_se3mpc_solve_batch_host(const dart_se3mpc_params *params, int64_t B,
     const size_t Bp = staged ? (size_t)((B + 3) / 4 * 4) : (size_t)((B + 31) / 32 * 32);
     const WsLayout L((int)N, Bp);
     cudaError_t e;
+    {
+        int dev = 0;
+        e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) {
+            set_err(e, "cudaGetDevice");
+            return DART_E_NODEVICE;
+        }
+        if (g_ws.device != dev) { /* the calling thread moved to another GPU: start over there */
+            if (g_ws.device >= 0) {
+                cudaSetDevice(g_ws.device);
+                if (g_ws.dev) cudaFree(g_ws.dev);
+                if (g_ws.stream) cudaStreamDestroy(g_ws.stream);
+                if (g_ws.stream2) cudaStreamDestroy(g_ws.stream2);
+                cudaSetDevice(dev);
+            }
+            g_ws.dev = nullptr;
+            g_ws.cap = 0;
+            g_ws.stream = g_ws.stream2 = nullptr;
+            g_ws.device = dev;
+        }
+    }
     if (!g_ws.stream) {
         e = cudaStreamCreateWithFlags(&g_ws.stream, cudaStreamNonBlocking);
         if (e != cudaSuccess) return set_err(e, "cudaStreamCreate");

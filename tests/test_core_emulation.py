@@ -85,3 +85,36 @@ def test_core_grid_penalty_mode_matches_oracle(oracle_mod):
         assert (np.abs(got.x - ref.x).max(axis=1)[same] < 1e-6).all()
         relf = np.abs(got.cost - ref.cost) / np.maximum(np.abs(ref.cost), 1.0)
         assert (relf[same] < 1e-9).all()
+
+
+def test_core_random_configurations(oracle_mod, policy):
+    """Randomised config / airframe parameters, cold and warm, kernel core (all build policies)
+    against the oracle."""
+    import emu
+    from dart_planner_b200.config import SE3MPCConfig, make_params
+    rng = np.random.default_rng(77)
+    for trial in range(10):
+        N = int(rng.choice([3, 6, 8, 12, 20]))
+        kw = dict(max_velocity=float(rng.uniform(3, 15)), max_thrust=float(rng.uniform(18, 40)),
+                  min_thrust=float(rng.uniform(0.5, 4)), max_tilt_angle=float(rng.uniform(0.3, 1.2)),
+                  position_weight=float(rng.uniform(10, 300)), velocity_weight=float(rng.uniform(1, 30)),
+                  acceleration_weight=float(rng.uniform(0.2, 5)), thrust_weight=float(rng.uniform(0.02, 1)),
+                  max_iterations=int(rng.integers(2, 20)), convergence_tolerance=float(rng.choice([0.1, 0.05, 0.01])))
+        dt = float(rng.choice([0.0025, 0.05, 0.1]))
+        mass = float(rng.uniform(0.6, 3.0))
+        B = 200
+        p0 = rng.uniform(-10, 10, (B, 3))
+        v0 = rng.uniform(-3, 3, (B, 3))
+        goal = np.concatenate([rng.uniform(-15, 15, (B, 2)), rng.uniform(2, 9, (B, 1))], axis=1)
+        op = oracle_mod.make_params(horizon=N, dt=dt, mass=mass, **kw)
+        pr = make_params(SE3MPCConfig(prediction_horizon=N, dt=dt, **kw), mass=mass)
+        for xw in (None, "warm"):
+            if xw == "warm":
+                xw = ref.x.copy()
+                xw[:, 6 * N:] += rng.normal(0, 0.3, xw[:, 6 * N:].shape)
+            ref = oracle_mod.solve_batch(op, p0, v0, goal, x_warm=xw, nthreads=8)
+            got = emu.solve_batch(pr, p0, v0, goal, x_warm=xw)
+            same = (got.nit == ref.nit) & (got.nfev == ref.nfev) & (got.status == ref.status)
+            assert same.mean() >= 0.99, (trial, N, kw)
+            assert (np.abs(got.x - ref.x).max(axis=1)[same] < 1e-6).all()
+            np.testing.assert_allclose(got.attitudes[same], ref.attitudes[same], atol=1e-6)

@@ -343,3 +343,36 @@ def test_gpu_build_variants_agree(oracle_mod, monkeypatch):
         np.testing.assert_array_equal(got.nfev, base.nfev)
         np.testing.assert_array_equal(got.status, base.status)
         np.testing.assert_allclose(got.body_rates, base.body_rates, rtol=0, atol=1e-9)
+
+
+def test_gpu_random_configurations(oracle_mod):
+    """Randomised SE3MPCConfig / airframe parameters (weights, bounds, tilt, mass, horizon, dt,
+    tolerance, iteration cap), warm and cold, against the oracle: the kernel reads every parameter
+    the reference solve reads."""
+    import dart_planner_b200 as dp
+    rng = np.random.default_rng(2024)
+    for trial in range(16):
+        N = int(rng.choice([3, 5, 6, 8, 10, 16, 24]))
+        kw = dict(max_velocity=float(rng.uniform(3, 15)), max_thrust=float(rng.uniform(18, 40)),
+                  min_thrust=float(rng.uniform(0.5, 4)), max_tilt_angle=float(rng.uniform(0.3, 1.2)),
+                  position_weight=float(rng.uniform(10, 300)), velocity_weight=float(rng.uniform(1, 30)),
+                  acceleration_weight=float(rng.uniform(0.2, 5)), thrust_weight=float(rng.uniform(0.02, 1)),
+                  max_iterations=int(rng.integers(2, 20)), convergence_tolerance=float(rng.choice([0.1, 0.05, 0.01])))
+        dt = float(rng.choice([0.0025, 0.05, 0.1, 0.2]))
+        mass = float(rng.uniform(0.6, 3.0))
+        B = 384
+        p0 = rng.uniform(-10, 10, (B, 3))
+        v0 = rng.uniform(-3, 3, (B, 3))
+        goal = np.concatenate([rng.uniform(-15, 15, (B, 2)), rng.uniform(2, 9, (B, 1))], axis=1)
+        cfg = dp.SE3MPCConfig(prediction_horizon=N, dt=dt, **kw)
+        op = oracle_mod.make_params(horizon=N, dt=dt, mass=mass, **kw)
+        ref = oracle_mod.solve_batch(op, p0, v0, goal, nthreads=16)
+        sol = dp.plan_batch(p0, v0, goal, cfg, mass=mass, to_host=True)
+        _compare(sol, ref, min_counter_agreement=0.99)
+        # warm start from the cold solution with a tilted thrust history
+        xw = ref.x.copy()
+        xw[:, 6 * N:] += rng.normal(0, 0.3, xw[:, 6 * N:].shape)
+        ref_w = oracle_mod.solve_batch(op, p0 + 0.1, v0, goal, x_warm=xw, nthreads=16)
+        sol_w = dp.plan_batch(p0 + 0.1, v0, goal, cfg, mass=mass, x_warm=xw, to_host=True)
+        _compare(sol_w, ref_w, min_counter_agreement=0.99)
+        np.testing.assert_allclose(sol_w.body_rates, ref_w.body_rates, atol=1e-4 / dt * 1e-2 + 1e-6, rtol=1e-6)

@@ -129,10 +129,13 @@ class BatchSolution:
         return self.first_hit < 0
 
     def numpy(self) -> "HostSolution":
-        """Copy everything to host ndarrays with the reference's shapes."""
-        out = self.out[:, : self.B].cpu().numpy()
+        """Copy everything to host ndarrays with the reference's shapes.  The SoA block is
+        transposed on the device (one pass over HBM instead of seven strided NumPy transposes on
+        the host); the result's fields are views of one (B, 19N+1) host array, like the
+        reference's views into ``result.x``."""
+        out_t = self.out[:, : self.B].t().contiguous().cpu().numpy()
         meta = self.meta[:, : self.B].cpu().numpy()
-        hs = HostSolution.from_blocks(self.N, out, meta)
+        hs = HostSolution.from_rows(self.N, out_t, meta)
         if self.hit is not None:
             hs.first_hit = self.hit[: self.B].cpu().numpy()
         return hs
@@ -164,6 +167,19 @@ class HostSolution:
             nfev=meta[1].copy(), status=meta[2].copy(), task=meta[3].copy(),
             accelerations=bn3(9 * N + 1), attitudes=bn3(12 * N + 1), body_rates=bn3(15 * N + 1),
             thrusts=np.ascontiguousarray(out[18 * N + 1: 19 * N + 1].T))
+
+    @staticmethod
+    def from_rows(N: int, rows: np.ndarray, meta: np.ndarray) -> "HostSolution":
+        """rows: (B, 19N+1) problem-major array [x 9N | cost | acc 3N | att 3N | rates 3N | thrust N]."""
+        B = rows.shape[0]
+
+        def bn3(lo):
+            return rows[:, lo:lo + 3 * N].reshape(B, N, 3)
+
+        return HostSolution(
+            x=rows[:, : 9 * N], cost=rows[:, 9 * N], nit=meta[0], nfev=meta[1], status=meta[2],
+            task=meta[3], accelerations=bn3(9 * N + 1), attitudes=bn3(12 * N + 1),
+            body_rates=bn3(15 * N + 1), thrusts=rows[:, 18 * N + 1: 19 * N + 1])
 
     @property
     def positions(self):

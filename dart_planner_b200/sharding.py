@@ -117,4 +117,6 @@ class ShardedSolver:
         if rank != self.dst:
             return None
         N = int(self.params.horizon)
+        if out.is_cuda:      # transpose on the device, one contiguous read-back
+            return HostSolution.from_rows(N, out.t().contiguous().cpu().numpy(), meta.cpu().numpy())
         return HostSolution.from_blocks(N, out.cpu().numpy(), meta.cpu().numpy())

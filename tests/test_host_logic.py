@@ -114,3 +114,20 @@ def test_no_cpu_fallback_without_cuda():
     import dart_planner_b200 as dp
     with pytest.raises(RuntimeError, match="CUDA"):
         dp.plan_batch(np.zeros((2, 3)), np.zeros((2, 3)), np.ones((2, 3)))
+
+
+def test_integration_stub_matches_the_header():
+    """The ctypes structure printed in INTEGRATION.md (what a maintainer of the reference would
+    paste) has exactly the fields of dart_se3mpc_params, in order."""
+    from dart_planner_b200 import _cabi
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = doc[doc.index("class _Params(C.Structure)"):doc.index("def _solve_se3_mpc(self, current_state)")]
+    names = re.findall(r'"([a-z_0-9]+)"', block)
+    assert names == [f for f, _ in _cabi.Params._fields_]
+    hdr = open(os.path.join(ROOT, "include", "dart_se3mpc.h")).read()
+    struct = hdr[hdr.index("typedef struct dart_se3mpc_params {"):hdr.index("} dart_se3mpc_params;")]
+    struct = re.sub(r"/\*.*?\*/", "", struct, flags=re.S)
+    declared = []
+    for decl in re.findall(r"(?:int32_t|double)\s+([^;]+);", struct):
+        declared += [n.strip() for n in decl.split(",")]
+    assert declared == names

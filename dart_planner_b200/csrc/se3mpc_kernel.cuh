@@ -194,5 +194,7 @@ KernelSet kernel_set_l32();
 KernelSet kernel_set_l32x2();
 KernelSet kernel_set_l8_occ3();
 KernelSet kernel_set_l8_b64();
+KernelSet kernel_set_l16_occ3();
+KernelSet kernel_set_l32_occ3();
 
 } /* namespace dartb200 */

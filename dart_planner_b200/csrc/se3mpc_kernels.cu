@@ -51,6 +51,8 @@ KernelChoice g_kernels[] = {
     /* [5] the 168-register throughput build for N <= 8 (3 resident blocks per SM); [6] tuning
      * variant (64-thread blocks), DART_SE3MPC_VARIANT=<index> (tools/kbench.py) */
     make_choice(kernel_set_l8_occ3()), make_choice(kernel_set_l8_b64()),
+    /* [7], [8] throughput builds for 8 < N <= 16 and 16 < N <= 32 */
+    make_choice(kernel_set_l16_occ3()), make_choice(kernel_set_l32_occ3()),
 };
 std::mutex g_mu;
 int g_sms = 0;
@@ -74,6 +76,8 @@ KernelChoice *pick_kernel(int N, long long B)
      * few spills for 50 % more warps in flight: +15 % at 64 Ki and 1 Mi problems, but -12 % on a
      * single round, where nothing waits for a free slot (profiles/README.md) */
     if (idx == 1 && N > 4 && B >= 16384) idx = 5;
+    if (idx == 2 && B >= 8192) idx = 7;
+    if (idx == 3 && B >= 8192) idx = 8;
     if (const char *v = getenv("DART_SE3MPC_VARIANT")) {
         const int want = atoi(v);
         const int nk = (int)(sizeof(g_kernels) / sizeof(g_kernels[0]));

@@ -60,6 +60,23 @@ def test_gpu_matches_oracle_random(oracle_mod, N, dt, seed, vs):
     _compare(sol, ref)
 
 
+@pytest.mark.parametrize("N,seed", [(13, 41), (32, 42)])
+def test_gpu_throughput_builds_wide_lanes(oracle_mod, N, seed):
+    """>= 8192 problems at 8 < N <= 32 run on the 168-register builds of the 16- / 32-lane
+    configurations."""
+    import dart_planner_b200 as dp
+    B = 8192 + 40
+    p0, v0, goal = bench_inputs(seed, B, 2.0)
+    ref = oracle_mod.solve_batch(oracle_mod.make_params(horizon=N, dt=0.1), p0, v0, goal, nthreads=16)
+    sol = dp.plan_batch(p0, v0, goal, dp.SE3MPCConfig(prediction_horizon=N, dt=0.1), to_host=True)
+    _compare(sol, ref)
+    xw = ref.x.copy()
+    xw[:, 6 * N:] += np.random.default_rng(seed).normal(0, 0.4, xw[:, 6 * N:].shape)
+    ref_w = oracle_mod.solve_batch(oracle_mod.make_params(horizon=N, dt=0.1), p0, v0, goal, x_warm=xw, nthreads=16)
+    sol_w = dp.plan_batch(p0, v0, goal, dp.SE3MPCConfig(prediction_horizon=N, dt=0.1), x_warm=xw, to_host=True)
+    _compare(sol_w, ref_w, min_counter_agreement=0.995)
+
+
 def test_gpu_near_goal_regime(oracle_mod):
     """Degenerate regime (line search fails, ABNORMAL endings): decisions sit on rounding
     noise, so a small fraction of counter differences is tolerated and reported."""

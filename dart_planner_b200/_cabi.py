@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdart_se3mpc.so")
+LIB_PATH = os.environ.get("DART_SE3MPC_LIB") or os.path.join(_HERE, "lib", "libdart_se3mpc.so")  # env: A/B builds
 
 DART_OK, DART_E_BADARG, DART_E_UNSUPPORTED, DART_E_CUDA, DART_E_NODEVICE = 0, -1, -2, -3, -4
 TASK_NAMES = {

@@ -21,7 +21,8 @@ variants = sys.argv[1].split(",") if len(sys.argv) > 1 else ["default"]
 Bs = [int(b) for b in sys.argv[2].split(",")] if len(sys.argv) > 2 else [4096, 65536]
 N = int(sys.argv[3]) if len(sys.argv) > 3 else 8
 L = _cabi.lib()
-params = make_params(dp.SE3MPCConfig(prediction_horizon=N, dt=0.1))
+params = make_params(dp.SE3MPCConfig(prediction_horizon=N, dt=0.1),
+                     max_corrections=int(os.environ.get("DART_KBENCH_M", "10")))
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 stream = torch.cuda.current_stream()
 for B in Bs:

@@ -420,6 +420,41 @@ def main():
         cl_ms = ea.elapsed_time(eb)
         others["configs[4] closed loop: 65536 drones x 100 replans (10 s at 10 Hz), warm starts, resident state"] = {
             "value": Bs * 100 / (cl_ms * 1e-3), "unit": UNIT, "total_ms": cl_ms, "launches": 100}
+        # mapper: one LiDAR-like scan (update_map) and the batched queries, the HBM/L2-bound side
+        rngm = np.random.default_rng(3)
+        R = 200_000
+        sensors = rngm.uniform(-10, 10, (8, 3))
+        rpos = sensors[rngm.integers(0, 8, R)]
+        rdir = rngm.normal(0, 1, (R, 3))
+        rhit = rngm.uniform(0.5, 30.0, R)
+        rhit[rngm.random(R) < 0.25] = np.nan
+        g2 = dp.DenseOccupancyGrid((256, 256, 256), (-128, -128, -128), 0.2, max_range=25.0)
+        g2.update_map(rpos, rdir, rhit, 30.0)                       # warm-up (allocates the counters)
+        torch.cuda.synchronize()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record(stream)
+        upd = g2.update_map(rpos, rdir, rhit, 30.0)
+        eb.record(stream)
+        torch.cuda.synchronize()
+        um_ms = ea.elapsed_time(eb)
+        ncell = 256 ** 3
+        others["mapper update_map: 200k rays into a 256^3 grid (ray walk + Bayes apply, incl. host staging of the scan)"] = {
+            "value": R / (um_ms * 1e-3), "unit": "rays/s", "total_ms": um_ms, "voxel_visits": upd["updated_voxels"],
+            "apply_pass_min_bytes": ncell * 12}
+        Q = 1 << 22
+        qpos = torch.as_tensor(rngm.uniform(-25, 25, (3, Q)), dtype=torch.float64, device="cuda")
+        qout = torch.empty(Q, dtype=torch.float64, device="cuda")
+        gq = g2._grid()
+        for _ in range(3):
+            L.dart_map_query_batch(C.byref(gq), Q, Q, qpos.data_ptr(), qout.data_ptr(), stream.cuda_stream)
+        ea.record(stream)
+        L.dart_map_query_batch(C.byref(gq), Q, Q, qpos.data_ptr(), qout.data_ptr(), stream.cuda_stream)
+        eb.record(stream)
+        torch.cuda.synchronize()
+        q_ms = ea.elapsed_time(eb)
+        others["mapper query_occupancy: 4 Mi random queries on the 256^3 grid"] = {
+            "value": Q / (q_ms * 1e-3), "unit": "queries/s", "kernel_ms": q_ms,
+            "hbm_frac_streaming_part": (Q * 32) / (q_ms * 1e-3) / 1e9 / hbm_peak}
         line["other_configs"] = others
         # single-solve latency through the drop-in planner (metric's second half)
         planner = dp.SE3MPCPlanner.from_yaml()

@@ -35,7 +35,25 @@ struct SolveArgs {
      * this library produced from cold starts): the 7-slot instantiation then serves warm starts
      * too.  The kernel checks the promise per problem and refuses (status 3) where it is broken. */
     int no_tilt_promise;
+    /* row output (off when rows == nullptr): every problem's whole result is ONE contiguous row
+     *   [x 9N | cost | acc 3N | att 3N | rates 3N | thrust N | int32 nit nfev status task first_hit 0]
+     * of row_stride doubles (a multiple of 16: whole 128-byte lines), staged in the problem's
+     * shared block and written with 16-byte stores, lane after lane -- the access pattern that
+     * lets `rows` be pinned HOST memory (zero-copy over PCIe) at close to the link rate.  The
+     * SoA output pointers above are ignored in this mode; first_hit != nullptr only switches the
+     * map check on. */
+    double *rows;
+    long long row_stride;
 };
+
+/* doubles of one result row (before padding) and the padded stride; 0 when the row does not fit
+ * the per-problem shared block it is staged in */
+__host__ __device__ inline int row_payload_doubles(int N) { return 19 * N + 4; }
+__host__ __device__ inline int row_stride_doubles(int N)
+{
+    const int st = (row_payload_doubles(N) + 15) / 16 * 16;
+    return st <= SM_DOUBLES ? st : 0;
+}
 
 template <int LANES, int TPL, int BLOCK, int MINB, int GM, bool TILT>
 __global__ void __launch_bounds__(BLOCK, MINB)
@@ -83,7 +101,17 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
                 for (int tt = 0; tt < TPL; ++tt)
                     tilted |= (sv.x[tt * 9 + 6] != 0.0 || sv.x[tt * 9 + 7] != 0.0) ? 1 : 0;
                 if (sv.grp.ori(tilted)) { /* broken promise: no solve, say so */
-                    if (sv.grp.leader()) {
+                    if ((MINB < 3) && A.rows) {
+                        double *row = A.rows + b * A.row_stride;
+                        for (int i = sv.grp.lane(); i < (int)A.row_stride; i += LANES)
+                            row[i] = (i == 9 * N) ? nan("") : 0.0;
+                        sv.grp.sync();
+                        if (sv.grp.leader()) {
+                            int *om = reinterpret_cast<int *>(row + 19 * N + 1);
+                            om[2] = 3;
+                            om[4] = -2;
+                        }
+                    } else if (sv.grp.leader()) {
                         if (A.status) A.status[b] = 3;
                         if (A.nit) A.nit[b] = 0;
                         if (A.nfev) A.nfev[b] = 0;
@@ -94,58 +122,89 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
             }
         } else
             sv.cold_start(p0, v0);
+        DP_TICK(0);
         SolveStats st;
         sv.minimize(st);
-        if (A.x_out) {
+        DP_TICK(40);
+        /* outputs: `emit` writes one problem's result through per-field base pointers with
+         * element stride `old` -- SoA rows of the batch (element b of every row, stride ld), or
+         * the staging row in this problem's shared block (stride 1; free now, the solve is
+         * over), which the group then copies out with full-line 16-byte stores.  Two inlined
+         * copies, so the SoA addressing stays what it was.  (The register-capped throughput
+         * builds leave the row mode out: the launcher sends row launches to the latency build,
+         * whose transfers are PCIe-bound anyway.) */
+        auto emit = [&](double *ox, double *ocost, double *oacc, double *oatt, double *orat, double *othr,
+                        int *onit, int *onfev, int *ostat, int *otask, int *ohit, const long long old,
+                        const bool check_map) {
+            if (ox) {
 #pragma unroll
-            for (int tt = 0; tt < TPL; ++tt)
-                if (sv.act[tt]) {
+                for (int tt = 0; tt < TPL; ++tt)
+                    if (sv.act[tt]) {
 #pragma unroll
-                    for (int q = 0; q < 9; ++q)
-                        A.x_out[(long long)sv.row_of(tt, q) * A.ld + b] = sv.x[tt * 9 + q];
-                }
-        }
-        if (sv.grp.leader()) {
-            if (A.cost) A.cost[b] = st.f;
-            if (A.nit) A.nit[b] = st.nit;
-            if (A.nfev) A.nfev[b] = st.nfev;
-            if (A.status) A.status[b] = st.status;
-            if (A.task) A.task[b] = st.task;
-        }
-        if (A.acc || A.att || A.rates || A.thrust) {
-            const SolveArgs &a = A;
-            sv.extract([&a, b](int k, double ax, double ay, double az, double r0, double r1,
-                               double r2, double w0, double w1, double w2, double th) {
-                const long long ld = a.ld;
-                if (a.acc) {
-                    a.acc[(long long)(3 * k) * ld + b] = ax;
-                    a.acc[(long long)(3 * k + 1) * ld + b] = ay;
-                    a.acc[(long long)(3 * k + 2) * ld + b] = az;
-                }
-                if (a.att) {
-                    a.att[(long long)(3 * k) * ld + b] = r0;
-                    a.att[(long long)(3 * k + 1) * ld + b] = r1;
-                    a.att[(long long)(3 * k + 2) * ld + b] = r2;
-                }
-                if (a.rates) {
-                    a.rates[(long long)(3 * k) * ld + b] = w0;
-                    a.rates[(long long)(3 * k + 1) * ld + b] = w1;
-                    a.rates[(long long)(3 * k + 2) * ld + b] = w2;
-                }
-                if (a.thrust) a.thrust[(long long)k * ld + b] = th;
-            });
-        }
-        if (A.first_hit) {
-            /* each lane tests its own timesteps against the map; the first colliding index is
-             * the minimum over the group (explicit_geometric_mapper.py:195-219) */
-            int hit = 0x7fffffff;
+                        for (int q = 0; q < 9; ++q) ox[(long long)sv.row_of(tt, q) * old] = sv.x[tt * 9 + q];
+                    }
+            }
+            if (sv.grp.leader()) {
+                if (ocost) *ocost = st.f;
+                if (onit) *onit = st.nit;
+                if (onfev) *onfev = st.nfev;
+                if (ostat) *ostat = st.status;
+                if (otask) *otask = st.task;
+            }
+            if (oacc || oatt || orat || othr) {
+                sv.extract([=](int k, double ax, double ay, double az, double r0, double r1, double r2,
+                               double w0, double w1, double w2, double th) {
+                    if (oacc) {
+                        oacc[(long long)(3 * k) * old] = ax;
+                        oacc[(long long)(3 * k + 1) * old] = ay;
+                        oacc[(long long)(3 * k + 2) * old] = az;
+                    }
+                    if (oatt) {
+                        oatt[(long long)(3 * k) * old] = r0;
+                        oatt[(long long)(3 * k + 1) * old] = r1;
+                        oatt[(long long)(3 * k + 2) * old] = r2;
+                    }
+                    if (orat) {
+                        orat[(long long)(3 * k) * old] = w0;
+                        orat[(long long)(3 * k + 1) * old] = w1;
+                        orat[(long long)(3 * k + 2) * old] = w2;
+                    }
+                    if (othr) othr[(long long)k * old] = th;
+                });
+            }
+            if (check_map) {
+                /* each lane tests its own timesteps against the map; the first colliding index is
+                 * the minimum over the group (explicit_geometric_mapper.py:195-219) */
+                int hit = 0x7fffffff;
 #pragma unroll
-            for (int tt = TPL - 1; tt >= 0; --tt)
-                if (sv.act[tt] && position_collides(A.grid, sv.x[tt * 9], sv.x[tt * 9 + 1], sv.x[tt * 9 + 2],
-                                                    A.margin, A.threshold))
-                    hit = sv.grp.lane() * TPL + tt;
-            hit = sv.grp.mini(hit);
-            if (sv.grp.leader()) A.first_hit[b] = (hit == 0x7fffffff) ? -1 : hit;
+                for (int tt = TPL - 1; tt >= 0; --tt)
+                    if (sv.act[tt] && position_collides(A.grid, sv.x[tt * 9], sv.x[tt * 9 + 1], sv.x[tt * 9 + 2],
+                                                        A.margin, A.threshold))
+                        hit = sv.grp.lane() * TPL + tt;
+                hit = sv.grp.mini(hit);
+                if (sv.grp.leader()) *ohit = (hit == 0x7fffffff) ? -1 : hit;
+            }
+        };
+        if ((MINB < 3) && A.rows != nullptr) {
+            sv.grp.sync();
+            double *oacc = sm + 9 * N + 1, *othr = oacc + 9 * N;
+            int *om = reinterpret_cast<int *>(othr + N);
+            for (int i = 19 * N + 3 + sv.grp.lane(); i < (int)A.row_stride; i += LANES) sm[i] = 0.0;
+            sv.grp.sync();
+            if (!A.first_hit && sv.grp.leader()) om[4] = -2; /* map check not requested */
+            emit(sm, sm + 9 * N, oacc, oacc + 3 * N, oacc + 6 * N, othr, om, om + 1, om + 2, om + 3, om + 4, 1,
+                 A.first_hit != nullptr);
+            sv.grp.sync();
+            double2 *dst = reinterpret_cast<double2 *>(A.rows + b * A.row_stride);
+            for (int i = sv.grp.lane(); i < (int)(A.row_stride >> 1); i += LANES)
+                dst[i] = make_double2(sm[2 * i], sm[2 * i + 1]);
+            sv.grp.sync();
+        } else {
+            emit(A.x_out ? A.x_out + b : nullptr, A.cost ? A.cost + b : nullptr, A.acc ? A.acc + b : nullptr,
+                 A.att ? A.att + b : nullptr, A.rates ? A.rates + b : nullptr,
+                 A.thrust ? A.thrust + b : nullptr, A.nit ? A.nit + b : nullptr, A.nfev ? A.nfev + b : nullptr,
+                 A.status ? A.status + b : nullptr, A.task ? A.task + b : nullptr,
+                 A.first_hit ? A.first_hit + b : nullptr, A.ld, A.first_hit != nullptr);
         }
         if (A.p_next && sv.grp.leader()) {
             /* reference planner model (se3_mpc_planner.py:430-431, :445-459) driven by T_0:
@@ -159,6 +218,7 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
                 A.v_next[c * A.ld + b] = DP_ADD(v0[c], DP_MUL(a, dt));
             }
         }
+        DP_TICK(41);
         (void)N;
     }
 }

@@ -181,6 +181,15 @@ class HostSolution:
             task=meta[3], accelerations=bn3(9 * N + 1), attitudes=bn3(12 * N + 1),
             body_rates=bn3(15 * N + 1), thrusts=rows[:, 18 * N + 1: 19 * N + 1])
 
+    @staticmethod
+    def from_packed_rows(N: int, rows: np.ndarray) -> "HostSolution":
+        """rows: (B, stride) float64 result rows of `dart_se3mpc_solve_batch_rows` (layout in
+        include/dart_se3mpc.h): views, no copies."""
+        meta = rows[:, 19 * N + 1: 19 * N + 4].view(np.int32)         # (B, 6)
+        sol = HostSolution.from_rows(N, rows, meta.T)
+        sol.first_hit = None if (meta[:, 4] == -2).all() else meta[:, 4]
+        return sol
+
     @property
     def positions(self):
         N = self.x.shape[1] // 9
@@ -282,7 +291,8 @@ class BatchWorkspace:
         self.x_warm = None
         self.warm_mask = None
         self.grid, self.safety_margin, self.collision_threshold, self.hit = None, 1.0, 0.6, None
-        self.h_inp = self.h_out = self.h_meta = None
+        self.h_inp = self.h_out = self.h_meta = self.h_rows = None
+        self.row_stride = int(_cabi.lib().dart_se3mpc_row_stride(C.byref(params)))
         if pinned:
             self.h_inp = torch.zeros((9, self.ld), dtype=torch.float64).pin_memory()
             self.h_out = torch.zeros((out_rows(self.N), self.ld), dtype=torch.float64).pin_memory()
@@ -372,6 +382,40 @@ class BatchWorkspace:
         stream.synchronize()
         return self.h_out, self.h_meta
 
+    @property
+    def rows_supported(self) -> bool:
+        return self.row_stride > 0 and self.h_inp is not None
+
+    @property
+    def d2h_bytes_rows(self) -> int:
+        return self.row_stride * 8 * self.B
+
+    def solve_rows(self, stream=None, wait: bool = True):
+        """Zero-copy end-to-end solve: ONE launch whose kernel reads the pinned input block and
+        writes every problem's result row straight into pinned host memory over PCIe (full
+        128-byte lines); no copy in either direction.  Returns the pinned (B, stride) row block
+        (`HostSolution.from_packed_rows(N, rows.numpy())` gives the named views)."""
+        torch = _torch()
+        if not self.rows_supported:
+            raise RuntimeError("row output needs pinned buffers and a horizon of at most 22 steps")
+        if self.h_rows is None:
+            self.h_rows = torch.zeros((self.ld, self.row_stride), dtype=torch.float64).pin_memory()
+        stream = stream or torch.cuda.current_stream(self.device)
+        es = 8 * self.ld
+        hi = self.h_inp.data_ptr()
+        g = self.grid._grid() if self.grid is not None else None
+        with torch.cuda.device(self.device):
+            rc = _cabi.lib().dart_se3mpc_solve_batch_rows(
+                C.byref(self.params), self.B, self.ld, hi, hi + 3 * es, hi + 6 * es,
+                _ptr(self.has_goal), _ptr(self.x_warm), _ptr(self.warm_mask),
+                self.h_rows.data_ptr(), self.row_stride,
+                C.byref(g) if g is not None else None, float(self.safety_margin),
+                float(self.collision_threshold), 1 if g is not None else 0, stream.cuda_stream)
+        _cabi.check(rc, "dart_se3mpc_solve_batch_rows")
+        if wait:
+            stream.synchronize()
+        return self.h_rows[: self.B]
+
     def _solve_staged_pipelined(self):
         """Large batches: the C host entry splits the batch into chunks on two streams so the
         read-back of one chunk overlaps the solve of the next (pinned buffers: fully async)."""
@@ -389,6 +433,8 @@ class BatchWorkspace:
 
     def solve_host(self, p0, v0, goal) -> HostSolution:
         self.stage_host_inputs(p0, v0, goal)
+        if self.rows_supported and self.B < 65536 and self.outputs == "all":
+            return HostSolution.from_packed_rows(self.N, self.solve_rows().numpy())
         h_out, h_meta = self.solve_staged()
         return HostSolution.from_blocks(self.N, h_out.numpy()[:, : self.B], h_meta.numpy()[:, : self.B])
 

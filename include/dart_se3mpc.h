@@ -132,6 +132,28 @@ int dart_se3mpc_solve_batch_map(const dart_se3mpc_params *params, int64_t B, int
                                 double margin, double threshold, int32_t *first_hit,
                                 void *cuda_stream);
 
+/* Row output: the same solve (and, with check_map != 0, the same fused safety check), with every
+ * problem's whole result written as ONE contiguous row -- the arrays the reference packs into
+ * the Trajectory it returns for one solve (se3_mpc_planner.py:656-675, from :582-654) next to
+ * the OptimizeResult fields it reads (:268-280):
+ *   double [0, 9N) x  (reference packed order [P | V | T], :361-376) | [9N] cost |
+ *   acc 3N | att 3N | rates 3N (entries 3k+c) | thrust N |
+ *   then int32 nit, nfev, status, task, first_hit (-1 safe, -2 not checked), 0
+ * i.e. 19N+4 doubles, padded with zeros to `row_stride` doubles.  row_stride must be a multiple
+ * of 16 (whole 128-byte lines), >= dart_se3mpc_row_stride(params), and `rows` 128-byte aligned.
+ * The kernel stages a row in shared memory and writes it with full-line 16-byte stores, so
+ * `rows` -- like p0/v0/goal/has_goal/x_warm -- may be mapped pinned HOST memory: the solve then
+ * needs no copy in either direction (the e2e path of BatchWorkspace.solve_rows, bench.py).
+ * dart_se3mpc_row_stride returns the minimal stride, or 0 when this horizon's row does not fit
+ * the staging block (N > 22): use the SoA entries then. */
+int64_t dart_se3mpc_row_stride(const dart_se3mpc_params *params);
+int dart_se3mpc_solve_batch_rows(const dart_se3mpc_params *params, int64_t B, int64_t ld,
+                                 const double *p0, const double *v0, const double *goal,
+                                 const uint8_t *has_goal, const double *x_warm,
+                                 const uint8_t *warm_mask, double *rows, int64_t row_stride,
+                                 const dart_grid *grid, double margin, double threshold,
+                                 int32_t check_map, void *cuda_stream);
+
 /* One replanning step of the closed-loop receding-horizon simulation (BASELINE configs[4]),
  * one launch: solve every problem from its resident state (p, v) -- cold start when warm == 0,
  * else the warm start of se3_mpc_planner.py:294-327 from the previous solution held in x --
@@ -148,8 +170,10 @@ int dart_se3mpc_closed_loop_step(const dart_se3mpc_params *params, int64_t B, in
                                  int32_t warm, double *cost, int32_t *nit, int32_t *nfev,
                                  int32_t *status, double plant_dt, void *cuda_stream);
 
-/* Same call with every buffer in HOST memory (pageable or pinned): stages through an
- * internal per-thread device workspace, copies in, solves, copies back and synchronises.
+/* Same call with every buffer in HOST memory (pageable or pinned).  Up to 512 problems go
+ * through a mapped pinned block the kernel reads and writes directly (no copies); larger batches
+ * stage through an internal per-thread device workspace (chunked on two streams from 65536
+ * problems up).  Returns after synchronising.
  * This is the plugin-level entry the drop-in planner's single-problem `plan()` uses. */
 int dart_se3mpc_solve_batch_host(const dart_se3mpc_params *params, int64_t B,
                                  const double *p0_host, const double *v0_host,

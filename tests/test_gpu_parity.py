@@ -409,3 +409,82 @@ def test_gpu_random_configurations(oracle_mod):
         ref_w = oracle_mod.solve_batch(op, p0 + 0.1, v0, goal, x_warm=xw, nthreads=16)
         sol_w = dp.plan_batch(p0 + 0.1, v0, goal, cfg, mass=mass, x_warm=xw, to_host=True)
         _compare_solutions(sol_w, ref_w, f"trial {trial} warm {kw}")
+
+
+@pytest.mark.parametrize("N,B", [(8, 4096), (8, 1), (6, 777), (3, 130), (13, 512), (20, 300)])
+def test_row_output_zero_copy_matches_soa_output(N, B):
+    """dart_se3mpc_solve_batch_rows: the kernel reads pinned host inputs and writes one packed row
+    per problem straight into pinned host memory (no copies).  Same bits as the SoA device path,
+    in every lane configuration, cold / warm / has_goal / map check."""
+    import dart_planner_b200 as dp
+    from dart_planner_b200.config import make_params
+    from dart_planner_b200.planner import BatchWorkspace, HostSolution
+    fields = ("x", "cost", "nit", "nfev", "status", "task", "accelerations", "attitudes", "body_rates", "thrusts")
+    p0, v0, goal = bench_inputs(100 + N, B, 2.0)
+    ws = BatchWorkspace(make_params(dp.SE3MPCConfig(prediction_horizon=N, dt=0.1)), B, pinned=True)
+    assert ws.rows_supported and ws.row_stride % 16 == 0 and ws.row_stride >= 19 * N + 4
+    ws.set_inputs_device(p0, v0, goal)
+    ws.stage_host_inputs(p0, v0, goal)
+    ref = ws.solve_device().numpy()
+    got = HostSolution.from_packed_rows(N, ws.solve_rows().numpy())
+    for f in fields:
+        np.testing.assert_array_equal(getattr(got, f), getattr(ref, f), err_msg=f)
+    assert got.first_hit is None
+    assert (ws.h_rows.numpy()[:B, 19 * N + 4:] == 0).all()              # padding is zeroed
+    # solve_host takes the row path below the pipelining threshold
+    host = ws.solve_host(p0, v0, goal)
+    np.testing.assert_array_equal(host.x, ref.x)
+    # warm start (tilted thrusts: 9-slot kernel) with a has_goal mask, plus the fused map check
+    rng = np.random.default_rng(N)
+    xprev = ref.x.copy()
+    xprev[:, 6 * N:] += rng.normal(0, 0.5, xprev[:, 6 * N:].shape)
+    hg = (np.arange(B) % 3 != 0).astype(np.uint8)
+    grid = dp.DenseOccupancyGrid((128, 128, 128), (-64, -64, -64), 0.4)
+    grid.add_obstacles(rng.uniform(-15, 15, (32, 3)), rng.uniform(0.8, 2.5, 32))
+    ws.set_warm(xprev)
+    ws.set_has_goal(hg)
+    ws.set_map(grid, 1.0, 0.6)
+    ref2 = ws.solve_device().numpy()
+    ws.h_rows.zero_()
+    got2 = HostSolution.from_packed_rows(N, ws.solve_rows().numpy())
+    for f in fields + ("first_hit",):
+        np.testing.assert_array_equal(getattr(got2, f), getattr(ref2, f), err_msg=f)
+    if B > 100:
+        assert (got2.first_hit >= 0).any() and (got2.first_hit == -1).any()
+
+
+def test_row_output_limits():
+    import ctypes as C
+    import torch
+    import dart_planner_b200 as dp
+    from dart_planner_b200 import _cabi
+    from dart_planner_b200.config import make_params
+    from dart_planner_b200.planner import BatchWorkspace
+    L = _cabi.lib()
+    assert L.dart_se3mpc_row_stride(C.byref(make_params(dp.SE3MPCConfig(prediction_horizon=8)))) == 160
+    assert L.dart_se3mpc_row_stride(C.byref(make_params(dp.SE3MPCConfig(prediction_horizon=22)))) == 432
+    # the row of a 40-step horizon does not fit the staging block: refused, SoA entries serve it
+    pr = make_params(dp.SE3MPCConfig(prediction_horizon=40, dt=0.1))
+    assert L.dart_se3mpc_row_stride(C.byref(pr)) == 0
+    ws = BatchWorkspace(pr, 8, pinned=True)
+    assert not ws.rows_supported
+    with pytest.raises(RuntimeError):
+        ws.solve_rows()
+    p0, v0, goal = bench_inputs(3, 8, 1.0)
+    assert ws.solve_host(p0, v0, goal).x.shape == (8, 360)               # falls back to the staged copies
+    # stride not a multiple of 16 / too small / misaligned rows: bad argument
+    pr = make_params(dp.SE3MPCConfig(prediction_horizon=8, dt=0.1))
+    inp = torch.zeros((9, 32), dtype=torch.float64, device="cuda")
+    rows = torch.zeros((32, 176), dtype=torch.float64, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+
+    def call(ptr, stride):
+        i = inp.data_ptr()
+        return L.dart_se3mpc_solve_batch_rows(C.byref(pr), 8, 32, i, i + 768, i + 1536, None, None, None,
+                                              ptr, stride, None, 0.0, 0.0, 0, s)
+    assert call(rows.data_ptr(), 176) == 0                                # device rows, wider stride: fine
+    assert call(rows.data_ptr(), 156) == -1
+    assert call(rows.data_ptr(), 144) == -1
+    assert call(rows.data_ptr() + 8, 160) == -1
+    assert call(None, 160) == -1
+    torch.cuda.synchronize()

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Kernel tuning bench: times the solve kernel for each DART_SE3MPC_VARIANT index on the bench
 distribution and checks every variant's result against variant-default (same arithmetic for the
-same lane count).  usage: python tools/kbench.py [variants=default,5,6,...] [B list] [N]"""
+same lane count).  usage: python tools/kbench.py [variants=default,5,6,...] [B list] [N]
+DART_KBENCH_NOFLUSH=1 skips the L2 flush between launches (warm instruction / data caches)."""
 import ctypes as C
 import os
 import statistics
@@ -45,7 +46,10 @@ for B in Bs:
         torch.cuda.synchronize()
         ms = []
         for _ in range(reps):
-            flush.zero_()
+            if os.environ.get("DART_KBENCH_NOFLUSH"):
+                torch.cuda._sleep(400000)   # keeps the GPU busy while the launch is queued; L2 stays warm
+            else:
+                flush.zero_()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)
             ws.solve_device(stream)

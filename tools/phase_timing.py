@@ -20,7 +20,9 @@ NAMES = {0: "start: load inputs, cold start", 1: "begin: clip", 2: "begin: first
          16: "lnsrlb: d, dtd, step bound", 17: "line search: trial point + f", 18: "line search: exit",
          19: "NEW_X: projected gradient, tests, y", 30: "  formk: pair sums", 31: "  subsm: W'd sums",
          32: "  subsm: K^-1 solves", 33: "  subsm: step + projection", 40: "pair update + finish",
-         41: "epilogue: stores, SO(3) extraction"}
+         41: "epilogue: stores, SO(3) extraction", 49: "  cauchy: entry", 50: "  cauchy: per-variable pass",
+         51: "  cauchy: breakpoint count (reduction)", 52: "  cauchy: closed-form pass",
+         53: "  cauchy: crossing count (reduction)"}
 
 
 def build():

@@ -397,7 +397,7 @@ class BatchWorkspace:
         (`HostSolution.from_packed_rows(N, rows.numpy())` gives the named views)."""
         torch = _torch()
         if not self.rows_supported:
-            raise RuntimeError("row output needs pinned buffers and a horizon of at most 22 steps")
+            raise RuntimeError("row output needs pinned buffers and a horizon of at most 25 steps")
         if self.h_rows is None:
             self.h_rows = torch.zeros((self.ld, self.row_stride), dtype=torch.float64).pin_memory()
         stream = stream or torch.cuda.current_stream(self.device)

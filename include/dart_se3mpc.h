@@ -145,7 +145,7 @@ int dart_se3mpc_solve_batch_map(const dart_se3mpc_params *params, int64_t B, int
  * `rows` -- like p0/v0/goal/has_goal/x_warm -- may be mapped pinned HOST memory: the solve then
  * needs no copy in either direction (the e2e path of BatchWorkspace.solve_rows, bench.py).
  * dart_se3mpc_row_stride returns the minimal stride, or 0 when this horizon's row does not fit
- * the staging block (N > 22): use the SoA entries then. */
+ * the staging block (N > 25): use the SoA entries then. */
 int64_t dart_se3mpc_row_stride(const dart_se3mpc_params *params);
 int dart_se3mpc_solve_batch_rows(const dart_se3mpc_params *params, int64_t B, int64_t ld,
                                  const double *p0, const double *v0, const double *goal,

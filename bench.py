@@ -396,6 +396,35 @@ def main():
                                "e2e_value": Bs / (statistics.mean(m2) * 1e-3)}
             del w2
         line["sweep"] = sweep
+        # the same workload as a stream of batches: launches queued back to back between ONE pair of
+        # events (no per-launch event/launch gap), cycling through enough resident input/output sets
+        # that a set has left the L2 before it comes round again (reported beside `value`, which
+        # keeps the per-launch events + L2 flush of the timing rules)
+        per_set = B * (9 + 19 * N + 1) * 8 + 4 * B * 4
+        nsets = max(2, -(-2 * 126 * (1 << 20) // per_set))
+        ring = []
+        for i in range(nsets):
+            w = BatchWorkspace(params, B, pinned=False, outputs="all")
+            w.set_inputs_device(p0, v0, goal)       # the named workload in every set
+            ring.append(w)
+        for w in ring:
+            w.solve_device(stream)
+        torch.cuda.synchronize()
+        k_chain = 4 * nsets
+        torch.cuda._sleep(2_000_000)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(k_chain):
+            ring[i % nsets].solve_device(stream)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        chain_ms = e0.elapsed_time(e1) / k_chain
+        line["back_to_back"] = {"value": B / (chain_ms * 1e-3), "unit": UNIT, "ms_per_step": chain_ms,
+                                "launches": k_chain, "resident_sets": nsets,
+                                "working_set_mb": nsets * per_set / 1e6,
+                                "note": "one event pair around the whole stream of launches; inputs rotate "
+                                        "through a working set larger than the L2"}
+        del ring
         # the other BASELINE configs, timed once each (kernel-only, resident inputs); their
         # parity lives in tests/test_gpu_config3.py and tests/test_gpu_closed_loop.py
         others = {}

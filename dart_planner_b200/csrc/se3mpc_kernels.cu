@@ -74,12 +74,15 @@ KernelChoice *pick_kernel(int N, long long B, bool rows = false)
     if (g_batch_hint > B) B = g_batch_hint;
     if (rows) B = 1; /* row output exists in the latency builds only */
     int idx = N <= 4 ? 0 : N <= 8 ? 1 : N <= 16 ? 2 : N <= 32 ? 3 : 4;
-    /* N <= 8, many rounds of work: the 168-register build (3 resident blocks per SM) trades a
-     * few spills for 50 % more warps in flight: +15 % at 64 Ki and 1 Mi problems, but -12 % on a
-     * single round, where nothing waits for a free slot (profiles/README.md) */
-    if (idx == 1 && N > 4 && B >= 16384) idx = 5;
-    if (idx == 2 && B >= 8192) idx = 7;
-    if (idx == 3 && B >= 8192) idx = 8;
+    /* N <= 8: the 168-register build (3 resident blocks per SM) trades a few spills for 50 % more
+     * warps in flight: +9 % at 64 Ki and 1 Mi problems, but -10 % on a single round, where
+     * nothing waits for a free slot.  It takes over as soon as the latency build (2 blocks of 16
+     * problems per SM) would need a second round: 6 144 problems are 43 us in one round of the
+     * throughput build against 54 us in two rounds of the latency build (profiles/README.md) */
+    const long long one_round = 2ll * (g_sms > 0 ? g_sms : 148) * 16;
+    if (idx == 1 && N > 4 && B > one_round) idx = 5;
+    if (idx == 2 && B >= 12288) idx = 7;
+    if (idx == 3 && B >= 12288) idx = 8;
     if (const char *v = getenv("DART_SE3MPC_VARIANT")) {
         const int want = atoi(v);
         const int nk = (int)(sizeof(g_kernels) / sizeof(g_kernels[0]));

@@ -62,10 +62,17 @@ def test_gpu_matches_oracle_random(oracle_mod, N, dt, seed, vs):
 
 @pytest.mark.parametrize("N,seed", [(13, 41), (32, 42)])
 def test_gpu_throughput_builds_wide_lanes(oracle_mod, N, seed):
-    """>= 8192 problems at 8 < N <= 32 run on the 168-register builds of the 16- / 32-lane
+    """>= 12288 problems at 8 < N <= 32 run on the 168-register builds of the 16- / 32-lane
     configurations."""
+    import ctypes as C
     import dart_planner_b200 as dp
-    B = 8192 + 40
+    from dart_planner_b200 import _cabi
+    from dart_planner_b200.config import make_params
+    B = 12288 + 40
+    regs = C.c_int32()
+    _cabi.lib().dart_se3mpc_kernel_info(C.byref(make_params(dp.SE3MPCConfig(prediction_horizon=N, dt=0.1))), B,
+                                        None, None, None, None, C.byref(regs))
+    assert regs.value <= 168
     p0, v0, goal = bench_inputs(seed, B, 2.0)
     ref = oracle_mod.solve_batch(oracle_mod.make_params(horizon=N, dt=0.1), p0, v0, goal, nthreads=16)
     sol = dp.plan_batch(p0, v0, goal, dp.SE3MPCConfig(prediction_horizon=N, dt=0.1), to_host=True)

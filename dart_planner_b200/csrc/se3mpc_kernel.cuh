@@ -227,6 +227,7 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
 struct KernelSet {
     const void *fn[3][2];
     int lanes, tpl, block, minb;
+    int resident; /* blocks per SM the shared-memory carve-out is sized for (default: minb) */
 };
 
 template <int LANES, int TPL, int MINB, int BLK>
@@ -243,6 +244,7 @@ KernelSet make_kernel_set()
     k.tpl = TPL;
     k.block = BLK;
     k.minb = MINB;
+    k.resident = MINB;
     return k;
 }
 

@@ -79,7 +79,7 @@ KernelChoice *pick_kernel(int N, long long B, bool rows = false)
      * nothing waits for a free slot.  It takes over as soon as the latency build (2 blocks of 16
      * problems per SM) would need a second round: 6 144 problems are 43 us in one round of the
      * throughput build against 54 us in two rounds of the latency build (profiles/README.md) */
-    const long long one_round = 2ll * (g_sms > 0 ? g_sms : 148) * 16;
+    const long long one_round = 2ll * (g_sms > 0 ? g_sms : 148) * 16; /* 2 blocks x 16 problems per SM */
     if (idx == 1 && N > 4 && B > one_round) idx = 5;
     if (idx == 2 && B >= 12288) idx = 7;
     if (idx == 3 && B >= 12288) idx = 8;
@@ -113,7 +113,7 @@ int prepare(KernelChoice *k)
     }
     /* shared-memory share of the 256 KB L1: what `minb` resident blocks need (+1 KB each that
      * the driver reserves); the rest stays L1 for the per-lane S/Y pairs in local memory */
-    int carve = (int)((long long)k->minb * (smem + 1024) * 100 / (228 * 1024)) + 1;
+    int carve = (int)((long long)k->set.resident * (smem + 1024) * 100 / (228 * 1024)) + 1;
     if (carve > 100) carve = 100;
     for (const void *fn : {k->set.fn[0][0], k->set.fn[0][1], k->set.fn[1][0], k->set.fn[1][1], k->set.fn[2][0], k->set.fn[2][1]}) {
         e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve);

@@ -428,7 +428,7 @@ int dart_se3mpc_solve_batch_host(const dart_se3mpc_params *params, int64_t B,
         if (g_ws.pin) cudaFreeHost(g_ws.pin);
         g_ws.pin = nullptr;
         g_ws.pin_cap = 0;
-        e = cudaHostAlloc(&g_ws.pin, L.bytes, cudaHostAllocMapped);
+        e = cudaHostAlloc(&g_ws.pin, L.bytes, cudaHostAllocMapped | cudaHostAllocPortable);
         if (e != cudaSuccess) return set_err(e, "cudaHostAlloc(staging)");
         g_ws.pin_cap = L.bytes;
     }

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Small fixed workload for ncu: `python tools/profile_case.py [B] [reps] [N]` launches the
-solve kernel `reps` times on the bench distribution (seed 1)."""
+"""Small fixed workload for ncu: `python tools/profile_case.py [B] [reps] [N] [rows]` launches the
+solve kernel `reps` times on the bench distribution (seed 1); with a fourth argument `rows` the
+launches are the zero-copy end-to-end ones (pinned host inputs, result rows into pinned host memory)."""
 import os
 import sys
 
@@ -19,9 +20,15 @@ N = int(sys.argv[3]) if len(sys.argv) > 3 else 8
 rng = np.random.default_rng(1)
 p0 = rng.uniform(-10, 10, (B, 3))
 goal = np.concatenate([rng.uniform(-15, 15, (B, 2)), rng.uniform(3, 8, (B, 1))], axis=1)
-ws = BatchWorkspace(make_params(dp.SE3MPCConfig(prediction_horizon=N, dt=0.1)), B, pinned=False)
+rows = len(sys.argv) > 4 and sys.argv[4] == "rows"
+ws = BatchWorkspace(make_params(dp.SE3MPCConfig(prediction_horizon=N, dt=0.1)), B, pinned=rows)
 ws.set_inputs_device(p0, np.zeros((B, 3)), goal)
+if rows:
+    ws.stage_host_inputs(p0, np.zeros((B, 3)), goal)
 for _ in range(reps):
-    ws.solve_device()
+    if rows:
+        ws.solve_rows()
+    else:
+        ws.solve_device()
 torch.cuda.synchronize()
 print("done", B, reps, float(ws.out[9 * N, :B].sum()))

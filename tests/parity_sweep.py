@@ -3,9 +3,9 @@
 `python tests/parity_sweep.py [seeds]` runs seeds x 12 random configurations (horizons 2..40,
 weights, bounds, dt, tolerance, iteration cap, up to 13 000 problems), cold and warm, and prints
 per case the fraction within the north-star tolerance and the fraction with equal counters.
-Cases flagged FAIL are the ones below the thresholds of tests/test_gpu_parity.py; so far every
-one of them is a configuration where the oracle disagrees with itself to the same extent after
-a one-ulp input change."""
+A case below the thresholds of tests/test_gpu_parity.py is re-examined: the oracle is run again
+with every start position (and warm-start entry) moved by one ulp, and the case only counts as a FAIL if the kernel
+agrees with the oracle worse than the oracle agrees with itself."""
 import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # tests/ -> repo root
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -44,7 +44,21 @@ for seed in range(int(sys.argv[1]) if len(sys.argv) > 1 else 6):
             same = (sol.nit == ref.nit) & (sol.nfev == ref.nfev) & (sol.status == ref.status)
             worst["ok"] = min(worst["ok"], ok.mean()); worst["same"] = min(worst["same"], same.mean())
             flag = "" if (ok.mean() >= 0.99 and ok[same].all() and same.mean() >= 0.85) else "  <-- FAIL"
-            bad += bool(flag)
+            if flag:
+                # is the oracle itself that sensitive here?  (one-ulp change of the start positions)
+                pin = p0 if mode == "cold" else p0 + 0.1
+                alt = oracle_mod.solve_batch(op, np.nextafter(pin, np.inf), v0, goal, nthreads=16,
+                                             **({} if mode == "cold" else {"x_warm": np.nextafter(xw, np.inf)}))
+                relf2 = np.abs(alt.cost - ref.cost) / np.maximum(np.abs(ref.cost), 1.0)
+                ok2 = (relf2 <= COST_RTOL) & (np.abs(alt.x - ref.x).max(axis=1) <= CTRL_ATOL)
+                same2 = (alt.nit == ref.nit) & (alt.nfev == ref.nfev) & (alt.status == ref.status)
+                slack = 2.0 / np.sqrt(B)     # sampling noise of a fraction over B problems
+                chaotic = ok.mean() >= ok2.mean() - 0.03 - slack and same.mean() >= same2.mean() - 0.06 - slack
+                flag = (f"  <-- below the test thresholds; oracle vs itself after one ulp: ok={ok2.mean():.4f} "
+                        f"same={same2.mean():.4f} -> {'chaotic configuration' if chaotic else 'FAIL'}")
+                bad += 0 if chaotic else 1
+            else:
+                bad += 0
             print(f"seed {seed} trial {trial} {mode} N={N} B={B} maxit={kw['max_iterations']} ok={ok.mean():.4f} same={same.mean():.4f} "
                   f"maxdx_same={dx[same].max() if same.any() else 0:.2e} nit_max={ref.nit.max()}{flag}", flush=True)
 print("worst", worst, "failures", bad)

@@ -396,6 +396,23 @@ def main():
                                "e2e_value": Bs / (statistics.mean(m2) * 1e-3)}
             del w2
         line["sweep"] = sweep
+        # end to end with controls rows (thrust vectors + cost + counters only: what a server that
+        # forwards thrust commands sends back), reported beside `e2e`, which returns whole trajectories
+        wc = BatchWorkspace(params, B, pinned=True, outputs="controls")
+        if wc.rows_supported:
+            wc.stage_host_inputs(p0, v0, goal)
+            sampler.active.set()
+            mc = time_steps(torch, lambda: wc.solve_rows(stream), flush, 50, 5, stream)
+            sampler.active.clear()
+            from dart_planner_b200.planner import HostSolution as _HS
+            gc = _HS.from_control_rows(N, wc.h_rows.numpy()[:B])
+            line["e2e_controls_rows"] = {
+                "value": B / (statistics.mean(mc) * 1e-3), "unit": UNIT, "ms_per_step": statistics.mean(mc),
+                "h2d_bytes_per_step": wc.h2d_bytes, "d2h_bytes_per_step": wc.d2h_bytes_rows,
+                "matches_resident_solve": bool(np.array_equal(gc.thrust_vectors, dev.thrust_vectors)
+                                               and np.array_equal(gc.nfev, dev.nfev)),
+                "api": "BatchWorkspace(outputs='controls').solve_rows"}
+        del wc
         # the same workload as a stream of batches: launches queued back to back between ONE pair of
         # events (no per-launch event/launch gap), cycling through enough resident input/output sets
         # that a set has left the L2 before it comes round again (reported beside `value`, which

@@ -90,9 +90,9 @@ def lib():
     L.dart_se3mpc_closed_loop_step.restype = C.c_int
     L.dart_se3mpc_solve_batch_host.argtypes = [C.POINTER(Params), i64] + [vp] * 14
     L.dart_se3mpc_solve_batch_host.restype = C.c_int
-    L.dart_se3mpc_row_stride.argtypes = [C.POINTER(Params)]
+    L.dart_se3mpc_row_stride.argtypes = [C.POINTER(Params), i32]
     L.dart_se3mpc_row_stride.restype = C.c_int64
-    L.dart_se3mpc_solve_batch_rows.argtypes = ([C.POINTER(Params), i64, i64] + [vp] * 7 + [i64] +
+    L.dart_se3mpc_solve_batch_rows.argtypes = ([C.POINTER(Params), i64, i64] + [vp] * 7 + [i64, i32] +
                                                [C.POINTER(Grid), C.c_double, C.c_double, i32, vp])
     L.dart_se3mpc_solve_batch_rows.restype = C.c_int
     L.dart_launch_count.restype = C.c_int64

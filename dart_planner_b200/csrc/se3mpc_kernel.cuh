@@ -44,14 +44,18 @@ struct SolveArgs {
      * map check on. */
     double *rows;
     long long row_stride;
+    /* 0: the full row above; 1: controls row [T 3N (rows 6N..9N of x) | cost | the same int32
+     * block with first_hit = -2] for callers that only forward the thrust commands: 3N+4 doubles
+     * (256 B at N=8 instead of 1 280 B over PCIe), no solution extraction, no map check */
+    int rows_kind;
 };
 
 /* doubles of one result row (before padding) and the padded stride; 0 when the row does not fit
  * the per-problem shared block it is staged in */
-__host__ __device__ inline int row_payload_doubles(int N) { return 19 * N + 4; }
-__host__ __device__ inline int row_stride_doubles(int N)
+__host__ __device__ inline int row_payload_doubles(int N, int kind) { return (kind == 1 ? 3 : 19) * N + 4; }
+__host__ __device__ inline int row_stride_doubles(int N, int kind)
 {
-    const int st = (row_payload_doubles(N) + 15) / 16 * 16;
+    const int st = (row_payload_doubles(N, kind) + 15) / 16 * 16;
     return st <= SM_DOUBLES ? st : 0;
 }
 
@@ -103,11 +107,12 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
                 if (sv.grp.ori(tilted)) { /* broken promise: no solve, say so */
                     if ((MINB < 3) && A.rows) {
                         double *row = A.rows + b * A.row_stride;
+                        const int nx = (A.rows_kind == 1 ? 3 : 9) * N, nd = (A.rows_kind == 1 ? 3 : 19) * N;
                         for (int i = sv.grp.lane(); i < (int)A.row_stride; i += LANES)
-                            row[i] = (i == 9 * N) ? nan("") : 0.0;
+                            row[i] = (i == nx) ? nan("") : 0.0;
                         sv.grp.sync();
                         if (sv.grp.leader()) {
-                            int *om = reinterpret_cast<int *>(row + 19 * N + 1);
+                            int *om = reinterpret_cast<int *>(row + nd + 1);
                             om[2] = 3;
                             om[4] = -2;
                         }
@@ -185,7 +190,33 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
                 if (sv.grp.leader()) *ohit = (hit == 0x7fffffff) ? -1 : hit;
             }
         };
-        if ((MINB < 3) && A.rows != nullptr) {
+        if ((MINB < 3) && A.rows != nullptr && A.rows_kind == 1) {
+            /* controls row: thrust vectors, cost, counters */
+            sv.grp.sync();
+            for (int i = 3 * N + sv.grp.lane(); i < (int)A.row_stride; i += LANES) sm[i] = 0.0;
+            sv.grp.sync();
+#pragma unroll
+            for (int tt = 0; tt < TPL; ++tt)
+                if (sv.act[tt]) {
+                    const int k = sv.grp.lane() * TPL + tt;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) sm[3 * k + c] = sv.x[tt * 9 + 6 + c];
+                }
+            if (sv.grp.leader()) {
+                int *om = reinterpret_cast<int *>(sm + 3 * N + 1);
+                sm[3 * N] = st.f;
+                om[0] = st.nit;
+                om[1] = st.nfev;
+                om[2] = st.status;
+                om[3] = st.task;
+                om[4] = -2;
+            }
+            sv.grp.sync();
+            double2 *dst = reinterpret_cast<double2 *>(A.rows + b * A.row_stride);
+            for (int i = sv.grp.lane(); i < (int)(A.row_stride >> 1); i += LANES)
+                dst[i] = make_double2(sm[2 * i], sm[2 * i + 1]);
+            sv.grp.sync();
+        } else if ((MINB < 3) && A.rows != nullptr) {
             sv.grp.sync();
             double *oacc = sm + 9 * N + 1, *othr = oacc + 9 * N;
             int *om = reinterpret_cast<int *>(othr + N);

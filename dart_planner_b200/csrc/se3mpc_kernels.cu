@@ -289,23 +289,25 @@ int dart_se3mpc_solve_batch(const dart_se3mpc_params *params, int64_t B, int64_t
                                        0.0, 0.0, nullptr, cuda_stream);
 }
 
-int64_t dart_se3mpc_row_stride(const dart_se3mpc_params *params)
+int64_t dart_se3mpc_row_stride(const dart_se3mpc_params *params, int32_t row_kind)
 {
-    if (check_params(params)) return 0;
-    return (int64_t)row_stride_doubles(params->horizon);
+    if (check_params(params) || row_kind < 0 || row_kind > 1) return 0;
+    return (int64_t)row_stride_doubles(params->horizon, row_kind);
 }
 
 int dart_se3mpc_solve_batch_rows(const dart_se3mpc_params *params, int64_t B, int64_t ld,
                                  const double *p0, const double *v0, const double *goal,
                                  const uint8_t *has_goal, const double *x_warm,
                                  const uint8_t *warm_mask, double *rows, int64_t row_stride,
-                                 const dart_grid *grid, double margin, double threshold,
-                                 int32_t check_map, void *cuda_stream)
+                                 int32_t row_kind, const dart_grid *grid, double margin,
+                                 double threshold, int32_t check_map, void *cuda_stream)
 {
     int rc = check_params(params);
     if (rc) return rc;
     if (B < 0 || ld < B || !p0 || !v0 || !goal || !rows) return DART_E_BADARG;
-    const int need = row_stride_doubles(params->horizon);
+    if (row_kind < 0 || row_kind > 1) return DART_E_BADARG;
+    if (row_kind == 1 && check_map) return DART_E_UNSUPPORTED; /* controls rows carry no map check */
+    const int need = row_stride_doubles(params->horizon, row_kind);
     if (need == 0) return DART_E_UNSUPPORTED; /* the row does not fit its staging block */
     if (row_stride < need || (row_stride & 15) != 0 || row_stride > SM_DOUBLES ||
         ((uintptr_t)rows & 127) != 0)
@@ -320,7 +322,7 @@ int dart_se3mpc_solve_batch_rows(const dart_se3mpc_params *params, int64_t B, in
     a.B = B; a.ld = ld;
     a.p0 = p0; a.v0 = v0; a.goal = goal; a.has_goal = has_goal;
     a.x_warm = x_warm; a.warm_mask = warm_mask;
-    a.rows = rows; a.row_stride = row_stride;
+    a.rows = rows; a.row_stride = row_stride; a.rows_kind = row_kind;
     if (need_grid) a.grid = *grid;
     if (check_map) {
         a.margin = margin;

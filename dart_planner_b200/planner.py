@@ -142,6 +142,21 @@ class BatchSolution:
 
 
 @dataclass
+class ControlsSolution:
+    """What a controls row carries: the thrust commands of every problem and the solver's report."""
+    thrust_vectors: np.ndarray
+    cost: np.ndarray
+    nit: np.ndarray
+    nfev: np.ndarray
+    status: np.ndarray
+    task: np.ndarray
+
+    @property
+    def success(self):
+        return self.status == 0
+
+
+@dataclass
 class HostSolution:
     x: np.ndarray
     cost: np.ndarray
@@ -189,6 +204,13 @@ class HostSolution:
         sol = HostSolution.from_rows(N, rows, meta.T)
         sol.first_hit = None if (meta[:, 4] == -2).all() else meta[:, 4]
         return sol
+
+    @staticmethod
+    def from_control_rows(N: int, rows: np.ndarray) -> "ControlsSolution":
+        """rows: (B, stride) controls rows (DART_ROWS_CONTROLS): views, no copies."""
+        meta = rows[:, 3 * N + 1: 3 * N + 4].view(np.int32)
+        return ControlsSolution(thrust_vectors=rows[:, : 3 * N].reshape(-1, N, 3), cost=rows[:, 3 * N],
+                                nit=meta[:, 0], nfev=meta[:, 1], status=meta[:, 2], task=meta[:, 3])
 
     @property
     def positions(self):
@@ -292,7 +314,8 @@ class BatchWorkspace:
         self.warm_mask = None
         self.grid, self.safety_margin, self.collision_threshold, self.hit = None, 1.0, 0.6, None
         self.h_inp = self.h_out = self.h_meta = self.h_rows = None
-        self.row_stride = int(_cabi.lib().dart_se3mpc_row_stride(C.byref(params)))
+        self.row_kind = 1 if outputs == "controls" else 0      # DART_ROWS_CONTROLS / DART_ROWS_FULL
+        self.row_stride = int(_cabi.lib().dart_se3mpc_row_stride(C.byref(params), self.row_kind))
         if pinned:
             self.h_inp = torch.zeros((9, self.ld), dtype=torch.float64).pin_memory()
             self.h_out = torch.zeros((out_rows(self.N), self.ld), dtype=torch.float64).pin_memory()
@@ -394,7 +417,9 @@ class BatchWorkspace:
         """Zero-copy end-to-end solve: ONE launch whose kernel reads the pinned input block and
         writes every problem's result row straight into pinned host memory over PCIe (full
         128-byte lines); no copy in either direction.  Returns the pinned (B, stride) row block
-        (`HostSolution.from_packed_rows(N, rows.numpy())` gives the named views)."""
+        (`HostSolution.from_packed_rows(N, rows.numpy())` gives the named views).  A workspace
+        built with ``outputs="controls"`` gets controls rows: thrust vectors, cost and counters
+        only (`HostSolution.from_control_rows`), a fifth of the bytes."""
         torch = _torch()
         if not self.rows_supported:
             raise RuntimeError("row output needs pinned buffers and a horizon of at most 25 steps")
@@ -408,7 +433,7 @@ class BatchWorkspace:
             rc = _cabi.lib().dart_se3mpc_solve_batch_rows(
                 C.byref(self.params), self.B, self.ld, hi, hi + 3 * es, hi + 6 * es,
                 _ptr(self.has_goal), _ptr(self.x_warm), _ptr(self.warm_mask),
-                self.h_rows.data_ptr(), self.row_stride,
+                self.h_rows.data_ptr(), self.row_stride, self.row_kind,
                 C.byref(g) if g is not None else None, float(self.safety_margin),
                 float(self.collision_threshold), 1 if g is not None else 0, stream.cuda_stream)
         _cabi.check(rc, "dart_se3mpc_solve_batch_rows")

@@ -144,15 +144,21 @@ int dart_se3mpc_solve_batch_map(const dart_se3mpc_params *params, int64_t B, int
  * The kernel stages a row in shared memory and writes it with full-line 16-byte stores, so
  * `rows` -- like p0/v0/goal/has_goal/x_warm -- may be mapped pinned HOST memory: the solve then
  * needs no copy in either direction (the e2e path of BatchWorkspace.solve_rows, bench.py).
- * dart_se3mpc_row_stride returns the minimal stride, or 0 when this horizon's row does not fit
- * the staging block (N > 25): use the SoA entries then. */
-int64_t dart_se3mpc_row_stride(const dart_se3mpc_params *params);
+ * row_kind 1 (DART_ROWS_CONTROLS): only what a caller forwarding thrust commands needs --
+ *   double [0, 3N) T (rows 6N..9N of x: the thrust vectors, :361-376) | [3N] cost |
+ *   the same six int32 (first_hit = -2) -- 3N+4 doubles (256 B instead of 1 280 B at N = 8);
+ *   no solution extraction is computed, check_map must be 0.
+ * dart_se3mpc_row_stride returns the minimal stride for the row kind, or 0 when this horizon's
+ * row does not fit the staging block (full rows: N > 25): use the SoA entries then. */
+#define DART_ROWS_FULL 0
+#define DART_ROWS_CONTROLS 1
+int64_t dart_se3mpc_row_stride(const dart_se3mpc_params *params, int32_t row_kind);
 int dart_se3mpc_solve_batch_rows(const dart_se3mpc_params *params, int64_t B, int64_t ld,
                                  const double *p0, const double *v0, const double *goal,
                                  const uint8_t *has_goal, const double *x_warm,
                                  const uint8_t *warm_mask, double *rows, int64_t row_stride,
-                                 const dart_grid *grid, double margin, double threshold,
-                                 int32_t check_map, void *cuda_stream);
+                                 int32_t row_kind, const dart_grid *grid, double margin,
+                                 double threshold, int32_t check_map, void *cuda_stream);
 
 /* One replanning step of the closed-loop receding-horizon simulation (BASELINE configs[4]),
  * one launch: solve every problem from its resident state (p, v) -- cold start when warm == 0,

@@ -468,11 +468,14 @@ def test_row_output_limits():
     from dart_planner_b200.config import make_params
     from dart_planner_b200.planner import BatchWorkspace
     L = _cabi.lib()
-    assert L.dart_se3mpc_row_stride(C.byref(make_params(dp.SE3MPCConfig(prediction_horizon=8)))) == 160
-    assert L.dart_se3mpc_row_stride(C.byref(make_params(dp.SE3MPCConfig(prediction_horizon=22)))) == 432
+    assert L.dart_se3mpc_row_stride(C.byref(make_params(dp.SE3MPCConfig(prediction_horizon=8))), 0) == 160
+    assert L.dart_se3mpc_row_stride(C.byref(make_params(dp.SE3MPCConfig(prediction_horizon=22))), 0) == 432
+    assert L.dart_se3mpc_row_stride(C.byref(make_params(dp.SE3MPCConfig(prediction_horizon=8))), 1) == 32
+    assert L.dart_se3mpc_row_stride(C.byref(make_params(dp.SE3MPCConfig(prediction_horizon=8))), 2) == 0
     # the row of a 40-step horizon does not fit the staging block: refused, SoA entries serve it
     pr = make_params(dp.SE3MPCConfig(prediction_horizon=40, dt=0.1))
-    assert L.dart_se3mpc_row_stride(C.byref(pr)) == 0
+    assert L.dart_se3mpc_row_stride(C.byref(pr), 0) == 0
+    assert L.dart_se3mpc_row_stride(C.byref(pr), 1) == 128            # controls rows fit up to N = 64
     ws = BatchWorkspace(pr, 8, pinned=True)
     assert not ws.rows_supported
     with pytest.raises(RuntimeError):
@@ -485,16 +488,51 @@ def test_row_output_limits():
     rows = torch.zeros((32, 176), dtype=torch.float64, device="cuda")
     s = torch.cuda.current_stream().cuda_stream
 
-    def call(ptr, stride):
+    def call(ptr, stride, kind=0, check_map=0):
         i = inp.data_ptr()
         return L.dart_se3mpc_solve_batch_rows(C.byref(pr), 8, 32, i, i + 768, i + 1536, None, None, None,
-                                              ptr, stride, None, 0.0, 0.0, 0, s)
+                                              ptr, stride, kind, None, 0.0, 0.0, check_map, s)
     assert call(rows.data_ptr(), 176) == 0                                # device rows, wider stride: fine
     assert call(rows.data_ptr(), 156) == -1
     assert call(rows.data_ptr(), 144) == -1
     assert call(rows.data_ptr() + 8, 160) == -1
     assert call(None, 160) == -1
+    assert call(rows.data_ptr(), 32, kind=1) == 0                         # controls rows
+    assert call(rows.data_ptr(), 16, kind=1) == -1
+    assert call(rows.data_ptr(), 160, kind=2) == -1
+    assert call(rows.data_ptr(), 32, kind=1, check_map=1) == -2           # no map check in controls rows
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("N,B", [(8, 4096), (6, 333), (4, 50), (13, 200), (40, 64)])
+def test_controls_rows_match_the_full_solution(N, B):
+    """DART_ROWS_CONTROLS: thrust vectors, cost and counters only, straight into pinned host memory
+    (a fifth of the bytes of a full row); same bits as the resident solve, cold and warm."""
+    import dart_planner_b200 as dp
+    from dart_planner_b200.config import make_params
+    from dart_planner_b200.planner import BatchWorkspace, HostSolution
+    p0, v0, goal = bench_inputs(200 + N, B, 2.0)
+    pr = make_params(dp.SE3MPCConfig(prediction_horizon=N, dt=0.1))
+    full = BatchWorkspace(pr, B, pinned=False)
+    full.set_inputs_device(p0, v0, goal)
+    ref = full.solve_device().numpy()
+    ws = BatchWorkspace(pr, B, pinned=True, outputs="controls")
+    assert ws.rows_supported and ws.row_stride == (3 * N + 4 + 15) // 16 * 16
+    ws.stage_host_inputs(p0, v0, goal)
+    got = HostSolution.from_control_rows(N, ws.solve_rows().numpy())
+    np.testing.assert_array_equal(got.thrust_vectors, ref.thrust_vectors)
+    np.testing.assert_array_equal(got.cost, ref.cost)
+    for f in ("nit", "nfev", "status", "task"):
+        np.testing.assert_array_equal(getattr(got, f), getattr(ref, f), err_msg=f)
+    assert (ws.h_rows.numpy()[:B, 3 * N + 1: 3 * N + 4].view(np.int32)[:, 4] == -2).all()
+    xw = ref.x.copy()
+    xw[:, 6 * N:] += np.random.default_rng(N).normal(0, 0.4, xw[:, 6 * N:].shape)
+    full.set_warm(xw)
+    ws.set_warm(xw)
+    ref_w = full.solve_device().numpy()
+    got_w = HostSolution.from_control_rows(N, ws.solve_rows().numpy())
+    np.testing.assert_array_equal(got_w.thrust_vectors, ref_w.thrust_vectors)
+    np.testing.assert_array_equal(got_w.nfev, ref_w.nfev)
 
 
 def test_gpu_chaotic_configuration_within_the_oracles_own_sensitivity(oracle_mod):

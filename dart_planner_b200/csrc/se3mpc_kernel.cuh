@@ -22,11 +22,12 @@ struct SolveArgs {
     double *x_out, *cost;
     int *nit, *nfev, *status, *task;
     double *acc, *att, *rates, *thrust;
-    /* fused post-solve safety check (is_trajectory_safe on the solved positions); off when
-     * first_hit == nullptr */
+    /* fused post-solve safety check (is_trajectory_safe on the solved positions); on when
+     * check_map != 0 */
     dart_grid grid;
     double margin, threshold;
     int *first_hit;
+    int check_map; /* 1: run the check (SoA mode: into first_hit; row mode: into the row) */
     /* fused plant step of the closed-loop simulation (off when p_next == nullptr): the state is
      * advanced with the first control of the new solution; may alias p0 / v0 */
     double *p_next, *v_next;
@@ -40,8 +41,8 @@ struct SolveArgs {
      * of row_stride doubles (a multiple of 16: whole 128-byte lines), staged in the problem's
      * shared block and written with 16-byte stores, lane after lane -- the access pattern that
      * lets `rows` be pinned HOST memory (zero-copy over PCIe) at close to the link rate.  The
-     * SoA output pointers above are ignored in this mode; first_hit != nullptr only switches the
-     * map check on. */
+     * SoA output pointers above are ignored in this mode (the map check's result goes into the
+     * row). */
     double *rows;
     long long row_stride;
     /* 0: the full row above; 1: controls row [T 3N (rows 6N..9N of x) | cost | the same int32
@@ -222,9 +223,9 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
             int *om = reinterpret_cast<int *>(othr + N);
             for (int i = 19 * N + 3 + sv.grp.lane(); i < (int)A.row_stride; i += LANES) sm[i] = 0.0;
             sv.grp.sync();
-            if (!A.first_hit && sv.grp.leader()) om[4] = -2; /* map check not requested */
+            if (!A.check_map && sv.grp.leader()) om[4] = -2; /* map check not requested */
             emit(sm, sm + 9 * N, oacc, oacc + 3 * N, oacc + 6 * N, othr, om, om + 1, om + 2, om + 3, om + 4, 1,
-                 A.first_hit != nullptr);
+                 A.check_map != 0);
             sv.grp.sync();
             double2 *dst = reinterpret_cast<double2 *>(A.rows + b * A.row_stride);
             for (int i = sv.grp.lane(); i < (int)(A.row_stride >> 1); i += LANES)
@@ -235,7 +236,7 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
                  A.att ? A.att + b : nullptr, A.rates ? A.rates + b : nullptr,
                  A.thrust ? A.thrust + b : nullptr, A.nit ? A.nit + b : nullptr, A.nfev ? A.nfev + b : nullptr,
                  A.status ? A.status + b : nullptr, A.task ? A.task + b : nullptr,
-                 A.first_hit ? A.first_hit + b : nullptr, A.ld, A.first_hit != nullptr);
+                 A.first_hit ? A.first_hit + b : nullptr, A.ld, A.check_map != 0 && A.first_hit != nullptr);
         }
         if (A.p_next && sv.grp.leader()) {
             /* reference planner model (se3_mpc_planner.py:430-431, :445-459) driven by T_0:

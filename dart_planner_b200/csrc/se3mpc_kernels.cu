@@ -252,6 +252,7 @@ int dart_se3mpc_solve_batch_map(const dart_se3mpc_params *params, int64_t B, int
         a.margin = margin;
         a.threshold = threshold;
         a.first_hit = first_hit;
+        a.check_map = 1;
     }
     return launch_solve(params, a, cuda_stream);
 }
@@ -327,7 +328,7 @@ int dart_se3mpc_solve_batch_rows(const dart_se3mpc_params *params, int64_t B, in
     if (check_map) {
         a.margin = margin;
         a.threshold = threshold;
-        a.first_hit = reinterpret_cast<int *>(rows); /* a flag in row mode: the result goes into the row */
+        a.check_map = 1; /* the result goes into the row */
     }
     return launch_solve(params, a, cuda_stream);
 }

@@ -130,8 +130,13 @@ class DenseOccupancyGrid:
         start = self._soa(positions, 3)
         d = self._soa(directions, 3)
         B = start.shape[1]
-        hit = np.array([np.nan if h is None else float(h) for h in np.asarray(hit_distances, object).reshape(-1)])
-        hit_t = torch.as_tensor(hit, dtype=torch.float64).to(self.device)
+        if torch.is_tensor(hit_distances):
+            hit_t = hit_distances.to(self.device, torch.float64).reshape(-1)
+        else:
+            hd = np.asarray(hit_distances)
+            if hd.dtype == object:      # the reference's Optional[float] per observation: None = no return
+                hd = np.array([np.nan if h is None else float(h) for h in hd.reshape(-1)])
+            hit_t = torch.as_tensor(np.ascontiguousarray(hd, np.float64).reshape(-1)).to(self.device)
         mr = torch.as_tensor(np.broadcast_to(np.asarray(max_ranges, np.float64), (B,)).copy()).to(self.device)
         if self._counts is None:
             self._counts = torch.zeros(self.nx * self.ny * self.nz, dtype=torch.int64, device=self.device)

@@ -178,23 +178,52 @@ __device__ __forceinline__ double bayes_update(double p, double lik)
     return fmin(fmax(p, 0.01), 0.99);
 }
 
+__device__ __forceinline__ void apply_cell(float *occ, unsigned long long *counts, long long i,
+                                           unsigned long long c, double lik_hit, double lik_miss)
+{
+    counts[i] = 0ull; /* leave the scratch zeroed for the next scan */
+    unsigned miss = (unsigned)(c & 0xffffffffull), hitn = (unsigned)(c >> 32);
+    double p = (double)occ[i];
+    /* 0.99 is a fixed point of both updates after the clip: 64 applications saturate */
+    if (miss > 64u) miss = 64u;
+    if (hitn > 64u) hitn = 64u;
+    /* an update that leaves p unchanged (the clip's fixed point) makes the rest of its run a
+     * no-op: stop there -- same result, ~12 instead of up to 64 updates per run */
+    for (unsigned k = 0; k < miss; ++k) {
+        const double pn = bayes_update(p, lik_miss);
+        if (pn == p) break;
+        p = pn;
+    }
+    for (unsigned k = 0; k < hitn; ++k) {
+        const double pn = bayes_update(p, lik_hit);
+        if (pn == p) break;
+        p = pn;
+    }
+    occ[i] = (float)p;
+}
+
+/* pass 2: a streaming read of the 8-byte counters (four cells = two 16-byte loads per thread and
+ * trip, so enough bytes are in flight to cover the HBM latency); untouched cells cost nothing more */
 __global__ void __launch_bounds__(256)
 map_apply_counts_kernel(float *occ, unsigned long long *counts, long long ncell, double lik_hit,
                         double lik_miss)
 {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ncell;
-         i += (long long)gridDim.x * blockDim.x) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nthr = (long long)gridDim.x * blockDim.x;
+    const bool aligned = (reinterpret_cast<unsigned long long>(counts) & 15ull) == 0ull;
+    const long long n4 = aligned ? ncell / 4 : 0;
+    const ulonglong2 *c2 = reinterpret_cast<const ulonglong2 *>(counts);
+    for (long long q = tid; q < n4; q += nthr) {
+        const ulonglong2 a = c2[2 * q], b = c2[2 * q + 1];
+        if ((a.x | a.y | b.x | b.y) == 0ull) continue;
+        if (a.x) apply_cell(occ, counts, 4 * q, a.x, lik_hit, lik_miss);
+        if (a.y) apply_cell(occ, counts, 4 * q + 1, a.y, lik_hit, lik_miss);
+        if (b.x) apply_cell(occ, counts, 4 * q + 2, b.x, lik_hit, lik_miss);
+        if (b.y) apply_cell(occ, counts, 4 * q + 3, b.y, lik_hit, lik_miss);
+    }
+    for (long long i = 4 * n4 + tid; i < ncell; i += nthr) {
         const unsigned long long c = counts[i];
-        if (c == 0ull) continue;
-        counts[i] = 0ull; /* leave the scratch zeroed for the next scan */
-        unsigned miss = (unsigned)(c & 0xffffffffull), hitn = (unsigned)(c >> 32);
-        double p = (double)occ[i];
-        /* 0.99 is a fixed point of both updates after the clip: 64 applications saturate */
-        if (miss > 64u) miss = 64u;
-        if (hitn > 64u) hitn = 64u;
-        for (unsigned k = 0; k < miss; ++k) p = bayes_update(p, lik_miss);
-        for (unsigned k = 0; k < hitn; ++k) p = bayes_update(p, lik_hit);
-        occ[i] = (float)p;
+        if (c) apply_cell(occ, counts, i, c, lik_hit, lik_miss);
     }
 }
 

@@ -49,6 +49,8 @@ struct SolveArgs {
      * block with first_hit = -2] for callers that only forward the thrust commands: 3N+4 doubles
      * (256 B at N=8 instead of 1 280 B over PCIe), no solution extraction, no map check */
     int rows_kind;
+    /* ticket counter of the dynamic schedule (zero at launch) */
+    unsigned long long *queue;
 };
 
 /* doubles of one result row (before padding) and the padded stride; 0 when the row does not fit
@@ -71,15 +73,11 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
     const int N = P.horizon;
     const long long stride = (long long)gridDim.x * GPB;
     double ws[MMAX][9 * TPL], wy[MMAX][9 * TPL]; /* per-lane S / Y pairs (local memory, L1) */
-    /* block-uniform trip count + a warp barrier per round: the sub-warps of a warp start every
-     * problem together (a sub-warp that converged early waits instead of running ahead into
-     * different code) */
-    (void)stride;
-    const long long rounds = (A.B + GPB - 1) / GPB;
-    for (long long blk = blockIdx.x; blk < rounds; blk += gridDim.x) {
-        __syncwarp();
-        const long long b = blk * GPB + gib;
-        if (b >= A.B) continue;
+    /* one problem, solved by this thread's sub-warp.  `alive` = false (lock-step builds only): a
+     * padding sub-warp that solves a copy of the last problem and writes nothing, so that every
+     * thread of the block reaches the block barriers */
+    auto solve_one = [&](const long long b, const bool alive) {
+        (void)alive;
         Solver<SubWarp<LANES>, TPL, GM, (MINB >= 3), TILT> sv(P, sm, ws, wy);
         if (GM == 2) {
             sv.obs.g = A.grid;
@@ -123,14 +121,27 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
                         if (A.nfev) A.nfev[b] = 0;
                         if (A.cost) A.cost[b] = nan("");
                     }
-                    continue;
+                    return;
                 }
             }
         } else
             sv.cold_start(p0, v0);
         DP_TICK(0);
         SolveStats st;
+#if defined(DART_LOCKSTEP)
+        /* the warps of a block start every iteration together: they run the same (mostly
+         * straight-line, executed-once) code at the same time and share its instruction fetches */
+        sv.begin();
+        for (;;) {
+            const int go = (sv.task == 0) ? 1 : 0;
+            if (!__syncthreads_or(go)) break;
+            if (go) sv.iterate();
+        }
+        sv.finish(st);
+        if (!alive) return;
+#else
         sv.minimize(st);
+#endif
         DP_TICK(40);
         /* outputs: `emit` writes one problem's result through per-field base pointers with
          * element stride `old` -- SoA rows of the batch (element b of every row, stride ld), or
@@ -252,7 +263,36 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
         }
         DP_TICK(41);
         (void)N;
+    };
+#if defined(DART_DYNQ)
+    /* dynamic schedule: a warp takes the next group of 32/LANES problems from a global ticket
+     * counter when it has finished its own, so no SM waits for the slowest static share */
+    constexpr int PPW = 32 / LANES;
+    const long long ntasks = (A.B + PPW - 1) / PPW;
+    for (;;) {
+        long long ti = 0;
+        if ((threadIdx.x & 31) == 0) ti = (long long)atomicAdd(A.queue, 1ull);
+        ti = __shfl_sync(0xffffffffu, ti, 0);
+        if (ti >= ntasks) break;
+        const long long b = ti * PPW + (threadIdx.x & 31) / LANES;
+        if (b < A.B) solve_one(b, true);
+        __syncwarp();
     }
+#else
+    /* block-uniform trip count + a warp barrier per round: the sub-warps of a warp start every
+     * problem together (a sub-warp that converged early waits instead of running ahead into
+     * different code) */
+    const long long rounds = (A.B + GPB - 1) / GPB;
+    for (long long blk = blockIdx.x; blk < rounds; blk += gridDim.x) {
+        __syncwarp();
+        const long long b = blk * GPB + gib;
+#if defined(DART_LOCKSTEP)
+        solve_one(b < A.B ? b : A.B - 1, b < A.B);
+#else
+        if (b < A.B) solve_one(b, true);
+#endif
+    }
+#endif
 }
 
 /* the six instantiations of one lane configuration: [gradient_mode][tilt] */

@@ -214,6 +214,14 @@ static int launch_solve(const dart_se3mpc_params *params, const SolveArgs &a, vo
     SolveArgs args_copy = a;
     void *args[] = {(void *)&P, (void *)&args_copy};
     const long long grid_blocks = grid_for(*k, a.B);
+#if defined(DART_DYNQ)
+    {
+        static thread_local unsigned long long *q = nullptr;
+        if (!q && cudaMalloc(&q, 64) != cudaSuccess) return DART_E_CUDA;
+        cudaMemsetAsync(q, 0, 8, (cudaStream_t)cuda_stream);
+        args_copy.queue = q;
+    }
+#endif
     const int cold = ((a.x_warm == nullptr || a.no_tilt_promise) && !getenv("DART_SE3MPC_NO_COLD")) ? 0 : 1;
     const void *fn = k->set.fn[params->gradient_mode][cold];
     cudaError_t e = cudaLaunchKernel(fn, dim3((unsigned)grid_blocks), dim3(k->block), args,

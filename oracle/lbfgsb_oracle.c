@@ -921,6 +921,22 @@ int orc_lbfgsb(int n, int m, double *x, const double *l, const double *u, const 
     nfev = 1;
     memcpy(xlast, x, sizeof(double) * n);
 
+    /* Non-finite start (behaviour of the reference recorded in tests/golden/nonfinite_*.npz,
+     * SciPy 1.18.1): a NaN in x0 survives the wrapper's clip, f is NaN, every trial of the first
+     * line search is rejected and after maxls of them the routine restores x0 and stops with
+     * ABNORMAL -- nit 0, status 2, fun NaN.  nfev = 1 + maxls, and one more when x itself
+     * holds a NaN: SciPy's evaluation cache compares x by value, a NaN never equals itself, so
+     * the wrapper's closing evaluation at the restored point counts as a new one. */
+    {
+        int xnan = 0;
+        for (int i = 0; i < n; ++i) xnan |= (x[i] != x[i]);
+        if (xnan || f != f) {
+            task = ORC_TASK_ABNORMAL;
+            nfev = 1 + maxls + (xnan ? 1 : 0);
+            goto done;
+        }
+    }
+
     sbgnrm = projgr(n, l, u, nbd, x, g);
     if (sbgnrm <= pgtol) {
         task = ORC_TASK_CONV_PGTOL;

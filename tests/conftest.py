@@ -41,14 +41,19 @@ CTRL_ATOL = 1e-4
 def assert_solution_parity(got, d, what=""):
     """got: object with x (B,9N), cost, nit, nfev, status, attitudes, body_rates, thrusts, accelerations."""
     fun = d["fun"]
-    relf = np.abs(np.asarray(got.cost) - fun) / np.maximum(np.abs(fun), 1.0)
-    dx = np.abs(np.asarray(got.x) - d["x"]).max(axis=1)
+    # non-finite fixtures (nonfinite_*.npz): NaNs must sit in exactly the same places
+    x_got, cost_got = np.asarray(got.x), np.asarray(got.cost)
+    assert np.array_equal(np.isnan(x_got), np.isnan(d["x"])), f"{what}: NaN pattern of x differs"
+    assert np.array_equal(np.isnan(cost_got), np.isnan(fun)), f"{what}: NaN pattern of the cost differs"
+    fun = np.nan_to_num(fun, nan=0.0)
+    relf = np.abs(np.nan_to_num(cost_got, nan=0.0) - fun) / np.maximum(np.abs(fun), 1.0)
+    dx = np.abs(np.nan_to_num(x_got, nan=0.0) - np.nan_to_num(d["x"], nan=0.0)).max(axis=1)
     bad = np.where((relf > COST_RTOL) | (dx > CTRL_ATOL))[0]
     assert bad.size == 0, f"{what}: {bad.size} problems out of tolerance, first {bad[:5]}, relf {relf[bad[:5]]}, dx {dx[bad[:5]]}"
     for k in ("nit", "nfev", "status"):
         mism = np.where(np.asarray(getattr(got, k)) != d[k])[0]
         assert mism.size == 0, f"{what}: {k} differs on {mism.size} problems, first {mism[:5]}: got {np.asarray(getattr(got, k))[mism[:5]]} want {d[k][mism[:5]]}"
-    np.testing.assert_allclose(got.accelerations, d["accelerations"], atol=1e-4 / 1.0, rtol=0)
+    np.testing.assert_allclose(got.accelerations, d["accelerations"], atol=1e-4 / 1.0, rtol=0)   # equal_nan
     np.testing.assert_allclose(got.thrusts, d["thrusts"], atol=1e-4, rtol=0)
     np.testing.assert_allclose(got.attitudes, d["attitudes"], atol=1e-6, rtol=0)
     # body rates are finite differences of R over dt: scale the tolerance by 1/dt

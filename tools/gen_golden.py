@@ -99,7 +99,7 @@ def solve_cases(N, dt, p0, v0, goal, has_goal=None, x_prev=None, **cfg):
         out["attitudes"][b] = sol["attitudes"]
         out["body_rates"][b] = sol["body_rates"]
         out["thrusts"][b] = sol["thrusts"]
-        assert np.array_equal(np.asarray(sol["thrust_vectors"]).ravel(), r.x[6 * N:])
+        assert np.array_equal(np.asarray(sol["thrust_vectors"]).ravel(), r.x[6 * N:], equal_nan=True)
     return out
 
 
@@ -196,6 +196,38 @@ def gen_solver():
     xprev = first["x"].copy()
     xprev[::3, 48:] += rng.normal(0, 1.0, xprev[::3, 48:].shape)
     save("warm_N8", solve_cases(8, 0.1, p1, v1, goal, x_prev=xprev))
+
+
+def gen_nonfinite():
+    """Non-finite states / goals / previous solutions: a NaN survives SciPy's clip of x0,
+    every line-search trial is rejected and the routine ends ABNORMAL at the start point (nit 0,
+    status 2, fun NaN, nfev = maxls + 1, + 1 when x itself holds a NaN: SciPy's evaluation cache
+    compares x by value); infinities are clipped to the bounds where the guess keeps them
+    infinite and become NaN where the guess forms inf - inf or 0 * inf."""
+    nan, inf = float("nan"), float("inf")
+    base = ([0.0, 0.0, 2.0], [0.0, 0.0, 0.0], [10.0, 0.0, 5.0])
+    cases = []
+    for which in range(3):
+        for comp in range(3):
+            for val in (nan, inf, -inf):
+                c = [list(base[0]), list(base[1]), list(base[2])]
+                c[which][comp] = val
+                cases.append(c)
+    p0 = np.array([c[0] for c in cases]); v0 = np.array([c[1] for c in cases]); goal = np.array([c[2] for c in cases])
+    with np.errstate(all="ignore"):
+        save("nonfinite_N8", solve_cases(8, 0.1, p0, v0, goal))
+        save("nonfinite_N6", solve_cases(6, 0.0025, p0[::2], v0[::2], goal[::2]))
+        # warm starts: NaN / inf inside the previous solution, NaN goal with a finite guess
+        first = solve_cases(8, 0.1, [base[0]], [base[1]], [base[2]])
+        xp = np.repeat(first["x"], 8, axis=0)
+        xp[1, 60] = nan          # T_4.x  (shifted into T_3)
+        xp[2, 5] = nan           # P_1.z
+        xp[3, 30] = inf          # V_2.x  (clipped to the bound)
+        xp[4, 71] = nan          # T_7.z
+        xp[5, 48] = nan          # T_0.x is dropped by the shift: a clean solve
+        xp[6, 0] = nan           # P_0 is replaced by the state: a clean solve
+        gw = np.tile(base[2], (8, 1)); gw[7, 1] = nan
+        save("nonfinite_warm_N8", solve_cases(8, 0.1, np.tile(base[0], (8, 1)), np.tile(base[1], (8, 1)), gw, x_prev=xp))
 
 
 def gen_extract():
@@ -313,7 +345,11 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "update_map":
         gen_update_map()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "nonfinite":
+        gen_nonfinite()
+        sys.exit(0)
     gen_solver()
+    gen_nonfinite()
     gen_extract()
     gen_mapper()
     gen_update_map()

@@ -83,7 +83,7 @@ class ClockSampler(threading.Thread):
         self.index = index
         self.samples, self.reasons = [], set()
         self.max_mhz = None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self.active = threading.Event()
         self.ok = False
         try:
@@ -106,7 +106,7 @@ class ClockSampler(threading.Thread):
             getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
             getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
         }
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             if self.active.is_set():
                 try:
                     self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
@@ -122,13 +122,36 @@ class ClockSampler(threading.Thread):
             time.sleep(0.002)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
+        if self.is_alive():
+            self.join(timeout=1.0)
 
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
         return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def time_python_reference(args, cores):
+    """The UNMODIFIED reference planner (baseline/_ref, staged by __graft_entry__.build()) on the
+    same workload, one process per host core: baseline/run_reference.py in a subprocess."""
+    import subprocess
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "baseline", "run_reference.py"),
+                            "--problems", str(args.batch), "--procs", str(cores), "--horizon", str(args.horizon),
+                            "--dt", str(args.dt), "--seed", "1"], capture_output=True, text=True, timeout=600)
+        out = json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:          # noqa: BLE001
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+    if "unavailable" in out:
+        return out
+    return {"value": out["value"], "unit": UNIT, "cores": out["procs"], "kind": "reference",
+            "sample": f"one pass over the same {args.batch}-problem workload, unmodified reference "
+                      "SE3MPCPlanner.plan_trajectory (pure Python + SciPy L-BFGS-B), one process per core",
+            "single_solve_ms": out["single_solve_ms"], "cpu_model": out["cpu_model"],
+            "per_core_solves_per_s": out["value"] / max(out["procs"], 1),
+            "g2_check": {"thrust_z": out["g2_thrust_z"], "expected": out["g2_expected_thrust_z"]}}
 
 
 def run_reference(args):
@@ -159,6 +182,9 @@ def run_reference(args):
                                    "se3_mpc_planner.py + L-BFGS-B, pthreads"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        # the reference's own Python path on the same workload and cores, reported beside the port
+        # (which is ~270x faster per core and is the arm the ratio is taken against)
+        "cpu_baseline_reference": time_python_reference(args, cores),
     }
     print(json.dumps(line), flush=True)
 
@@ -365,6 +391,7 @@ def main():
             "value": reps * B / cpu_dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{reps} passes over the same {B}-problem workload (~10 s), oracle/ C port of "
                       "se3_mpc_planner.py + SciPy L-BFGS-B semantics, pthreads"}
+        line["cpu_baseline_reference"] = time_python_reference(args, cores)
         flops_per_solve = r1.flops / B
         ach_tf = flops_per_solve * B / (kernel_ms * 1e-3) / 1e12
         roofline["fp64"] = {"achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",

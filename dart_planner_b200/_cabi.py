@@ -52,7 +52,7 @@ class Grid(C.Structure):
 EXPORTS = [
     "dart_abi_version", "dart_last_cuda_error", "dart_se3mpc_default_params",
     "dart_se3mpc_solve_batch", "dart_se3mpc_solve_batch_map", "dart_se3mpc_closed_loop_step",
-    "dart_se3mpc_solve_batch_host", "dart_se3mpc_row_stride", "dart_se3mpc_solve_batch_rows",
+    "dart_se3mpc_solve_batch_host", "dart_se3mpc_release_thread_workspace", "dart_se3mpc_row_stride", "dart_se3mpc_solve_batch_rows", "dart_se3mpc_extract_batch",
     "dart_launch_count",
     "dart_se3mpc_kernel_info", "dart_map_query_batch", "dart_map_traj_safe_batch",
     "dart_map_trace_ray_batch", "dart_map_update_batch", "dart_map_add_spheres", "dart_fp64_probe", "dart_ddiv_selftest",
@@ -90,6 +90,10 @@ def lib():
     L.dart_se3mpc_closed_loop_step.restype = C.c_int
     L.dart_se3mpc_solve_batch_host.argtypes = [C.POINTER(Params), i64] + [vp] * 14
     L.dart_se3mpc_solve_batch_host.restype = C.c_int
+    L.dart_se3mpc_extract_batch.argtypes = [C.POINTER(Params), i64, i64] + [vp] * 5 + [i32, vp]
+    L.dart_se3mpc_extract_batch.restype = C.c_int
+    L.dart_se3mpc_release_thread_workspace.argtypes = []
+    L.dart_se3mpc_release_thread_workspace.restype = None
     L.dart_se3mpc_row_stride.argtypes = [C.POINTER(Params), i32]
     L.dart_se3mpc_row_stride.restype = C.c_int64
     L.dart_se3mpc_solve_batch_rows.argtypes = ([C.POINTER(Params), i64, i64] + [vp] * 7 + [i64, i32] +

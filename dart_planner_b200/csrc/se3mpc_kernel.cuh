@@ -45,17 +45,22 @@ struct SolveArgs {
      * row). */
     double *rows;
     long long row_stride;
-    /* 0: the full row above; 1: controls row [T 3N (rows 6N..9N of x) | cost | the same int32
+    /* 0: the full row above; 2: solution row [x 9N | cost | the int32 block] (the derived arrays
+     * left out: 9N+4 doubles, 640 B at N=8); 1: controls row [T 3N (rows 6N..9N of x) | cost | the same int32
      * block with first_hit = -2] for callers that only forward the thrust commands: 3N+4 doubles
      * (256 B at N=8 instead of 1 280 B over PCIe), no solution extraction, no map check */
     int rows_kind;
-    /* ticket counter of the dynamic schedule (zero at launch) */
+    /* dynamic schedules: queue[0] ticket counter, queue[1] finished blocks; both zero at launch and
+     * re-armed by the last block of the launch */
     unsigned long long *queue;
 };
 
 /* doubles of one result row (before padding) and the padded stride; 0 when the row does not fit
  * the per-problem shared block it is staged in */
-__host__ __device__ inline int row_payload_doubles(int N, int kind) { return (kind == 1 ? 3 : 19) * N + 4; }
+__host__ __device__ inline int row_payload_doubles(int N, int kind)
+{
+    return (kind == 1 ? 3 : (kind == 2 ? 9 : 19)) * N + 4;
+}
 __host__ __device__ inline int row_stride_doubles(int N, int kind)
 {
     const int st = (row_payload_doubles(N, kind) + 15) / 16 * 16;
@@ -71,13 +76,33 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
     const int gib = threadIdx.x / LANES;
     double *sm = smem_all + gib * SM_DOUBLES;
     const int N = P.horizon;
-    const long long stride = (long long)gridDim.x * GPB;
     double ws[MMAX][9 * TPL], wy[MMAX][9 * TPL]; /* per-lane S / Y pairs (local memory, L1) */
+    /* How problems reach the sub-warps.
+     *   SCHED 0  static: block b takes rounds b, b + grid, ... of GPB problems (latency builds: one
+     *            round, nothing to balance).
+     *   SCHED 1  dynamic per warp: a warp takes the next 32/LANES problems from a global ticket
+     *            counter when it has finished its own, so no SM idles behind the slowest static share
+     *            (65 536 problems: 381 -> 296 us; the solves differ 3x in length; 1 Mi: 4.87 -> 4.57 ms).
+     *   SCHED 2  dynamic per block + lock step: the block takes GPB problems per ticket and its
+     *            warps start every L-BFGS-B iteration together (one barrier per iteration), so they
+     *            run the same straight-line code at the same time and share its instruction fetches
+     *            (65 536: 290 us; 1 Mi: 4.18 ms = 251 M solves/s.  Lock step on the static schedule,
+     *            SCHED 3, gives 376 us / 4.54 ms; in a single-round latency launch it only adds waiting).
+     * The throughput builds use DART_THROUGHPUT_SCHED (profiles/README.md, round 2). */
+#ifndef DART_THROUGHPUT_SCHED
+#define DART_THROUGHPUT_SCHED 2
+#endif
+#ifndef DART_LATENCY_SCHED
+#define DART_LATENCY_SCHED 0
+#endif
+    constexpr int SCHED = (MINB >= 3) ? DART_THROUGHPUT_SCHED : DART_LATENCY_SCHED;
+    constexpr bool LOCK = (SCHED == 2) || (SCHED == 3);
     /* one problem, solved by this thread's sub-warp.  `alive` = false (lock-step builds only): a
      * padding sub-warp that solves a copy of the last problem and writes nothing, so that every
      * thread of the block reaches the block barriers */
     auto solve_one = [&](const long long b, const bool alive) {
         (void)alive;
+        bool refused = false;
         Solver<SubWarp<LANES>, TPL, GM, (MINB >= 3), TILT> sv(P, sm, ws, wy);
         if (GM == 2) {
             sv.obs.g = A.grid;
@@ -106,7 +131,7 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
                 if (sv.grp.ori(tilted)) { /* broken promise: no solve, say so */
                     if ((MINB < 3) && A.rows) {
                         double *row = A.rows + b * A.row_stride;
-                        const int nx = (A.rows_kind == 1 ? 3 : 9) * N, nd = (A.rows_kind == 1 ? 3 : 19) * N;
+                        const int nx = (A.rows_kind == 1 ? 3 : 9) * N, nd = (A.rows_kind == 1 ? 3 : (A.rows_kind == 2 ? 9 : 19)) * N;
                         for (int i = sv.grp.lane(); i < (int)A.row_stride; i += LANES)
                             row[i] = (i == nx) ? nan("") : 0.0;
                         sv.grp.sync();
@@ -121,27 +146,27 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
                         if (A.nfev) A.nfev[b] = 0;
                         if (A.cost) A.cost[b] = nan("");
                     }
-                    return;
+                    refused = true;
                 }
             }
         } else
             sv.cold_start(p0, v0);
         DP_TICK(0);
         SolveStats st;
-#if defined(DART_LOCKSTEP)
-        /* the warps of a block start every iteration together: they run the same (mostly
-         * straight-line, executed-once) code at the same time and share its instruction fetches */
-        sv.begin();
-        for (;;) {
-            const int go = (sv.task == 0) ? 1 : 0;
-            if (!__syncthreads_or(go)) break;
-            if (go) sv.iterate();
+        if constexpr (LOCK) {
+            /* the warps of a block start every iteration together */
+            if (!refused) sv.begin();
+            for (;;) {
+                const int go = (!refused && sv.task == 0) ? 1 : 0;
+                if (!__syncthreads_or(go)) break;
+                if (go) sv.iterate();
+            }
+            if (refused || !alive) return;
+            sv.finish(st);
+        } else {
+            if (refused) return;
+            sv.minimize(st);
         }
-        sv.finish(st);
-        if (!alive) return;
-#else
-        sv.minimize(st);
-#endif
         DP_TICK(40);
         /* outputs: `emit` writes one problem's result through per-field base pointers with
          * element stride `old` -- SoA rows of the batch (element b of every row, stride ld), or
@@ -229,13 +254,17 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
                 dst[i] = make_double2(sm[2 * i], sm[2 * i + 1]);
             sv.grp.sync();
         } else if ((MINB < 3) && A.rows != nullptr) {
+            /* full row (kind 0) or solution row (kind 2: x, cost, counters -- the derived arrays
+             * are functions of the thrust rows of x and are left to the host) */
             sv.grp.sync();
+            const bool full = (A.rows_kind == 0);
             double *oacc = sm + 9 * N + 1, *othr = oacc + 9 * N;
-            int *om = reinterpret_cast<int *>(othr + N);
-            for (int i = 19 * N + 3 + sv.grp.lane(); i < (int)A.row_stride; i += LANES) sm[i] = 0.0;
+            int *om = reinterpret_cast<int *>(full ? othr + N : oacc);
+            for (int i = (full ? 19 : 9) * N + 3 + sv.grp.lane(); i < (int)A.row_stride; i += LANES) sm[i] = 0.0;
             sv.grp.sync();
             if (!A.check_map && sv.grp.leader()) om[4] = -2; /* map check not requested */
-            emit(sm, sm + 9 * N, oacc, oacc + 3 * N, oacc + 6 * N, othr, om, om + 1, om + 2, om + 3, om + 4, 1,
+            emit(sm, sm + 9 * N, full ? oacc : nullptr, full ? oacc + 3 * N : nullptr,
+                 full ? oacc + 6 * N : nullptr, full ? othr : nullptr, om, om + 1, om + 2, om + 3, om + 4, 1,
                  A.check_map != 0);
             sv.grp.sync();
             double2 *dst = reinterpret_cast<double2 *>(A.rows + b * A.row_stride);
@@ -264,40 +293,113 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
         DP_TICK(41);
         (void)N;
     };
-#if defined(DART_DYNQ)
-    /* dynamic schedule: a warp takes the next group of 32/LANES problems from a global ticket
-     * counter when it has finished its own, so no SM waits for the slowest static share */
-    constexpr int PPW = 32 / LANES;
-    const long long ntasks = (A.B + PPW - 1) / PPW;
-    for (;;) {
-        long long ti = 0;
-        if ((threadIdx.x & 31) == 0) ti = (long long)atomicAdd(A.queue, 1ull);
-        ti = __shfl_sync(0xffffffffu, ti, 0);
-        if (ti >= ntasks) break;
-        const long long b = ti * PPW + (threadIdx.x & 31) / LANES;
-        if (b < A.B) solve_one(b, true);
-        __syncwarp();
+    if constexpr (SCHED == 1) {
+        constexpr int PPW = 32 / LANES;
+        const long long ntasks = (A.B + PPW - 1) / PPW;
+        for (;;) {
+            long long ti = 0;
+            if ((threadIdx.x & 31) == 0) ti = (long long)atomicAdd(A.queue, 1ull);
+            ti = __shfl_sync(0xffffffffu, ti, 0);
+            if (ti >= ntasks) break;
+            const long long b = ti * PPW + (threadIdx.x & 31) / LANES;
+            if (b < A.B) solve_one(b, true);
+            __syncwarp();
+        }
+    } else if constexpr (SCHED == 2) {
+        __shared__ long long s_ticket;
+        const long long rounds = (A.B + GPB - 1) / GPB;
+        for (;;) {
+            __syncthreads();
+            if (threadIdx.x == 0) s_ticket = (long long)atomicAdd(A.queue, 1ull);
+            __syncthreads();
+            const long long blk = s_ticket;
+            if (blk >= rounds) break;
+            const long long b = blk * GPB + gib;
+            solve_one(b < A.B ? b : A.B - 1, b < A.B);
+        }
+    } else {
+        /* block-uniform trip count + a warp barrier per round: the sub-warps of a warp start every
+         * problem together (a sub-warp that converged early waits instead of running ahead into
+         * different code) */
+        const long long rounds = (A.B + GPB - 1) / GPB;
+        for (long long blk = blockIdx.x; blk < rounds; blk += gridDim.x) {
+            __syncwarp();
+            const long long b = blk * GPB + gib;
+            if constexpr (LOCK)
+                solve_one(b < A.B ? b : A.B - 1, b < A.B);
+            else if (b < A.B)
+                solve_one(b, true);
+        }
     }
-#else
-    /* block-uniform trip count + a warp barrier per round: the sub-warps of a warp start every
-     * problem together (a sub-warp that converged early waits instead of running ahead into
-     * different code) */
+    if constexpr (SCHED == 1 || SCHED == 2) {
+        /* the last block to finish re-arms the ticket counter for the next launch that uses it */
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(A.queue + 1, 1ull) == (unsigned long long)gridDim.x - 1ull) {
+                A.queue[0] = 0ull;
+                A.queue[1] = 0ull;
+                __threadfence();
+            }
+        }
+    }
+}
+
+/* Solution extraction alone (se3_mpc_planner.py:582-654 for B given thrust sequences): the
+ * solver's own `extract`, i.e. the code the solve kernel's epilogue runs, reachable with
+ * arbitrary thrust vectors (zero-thrust steps, degenerate b1, tilted sequences) that a solve
+ * only produces from special warm starts.  T: SoA rows 3k+c, row pitch ld. */
+struct ExtractArgs {
+    long long B, ld;
+    const double *T;
+    double *acc, *att, *rates, *thrust;
+};
+
+template <int LANES, int TPL, int BLOCK, bool TILT>
+__global__ void __launch_bounds__(BLOCK)
+se3mpc_extract_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_constant__ ExtractArgs A)
+{
+    constexpr int GPB = BLOCK / LANES;
+    const int gib = threadIdx.x / LANES;
     const long long rounds = (A.B + GPB - 1) / GPB;
     for (long long blk = blockIdx.x; blk < rounds; blk += gridDim.x) {
         __syncwarp();
         const long long b = blk * GPB + gib;
-#if defined(DART_LOCKSTEP)
-        solve_one(b < A.B ? b : A.B - 1, b < A.B);
-#else
-        if (b < A.B) solve_one(b, true);
-#endif
+        if (b < A.B) {
+            Solver<SubWarp<LANES>, TPL, 0, false, TILT> sv(P, nullptr, nullptr, nullptr);
+#pragma unroll
+            for (int tt = 0; tt < TPL; ++tt) {
+                const int k = sv.grp.lane() * TPL + tt;
+#pragma unroll
+                for (int q = 0; q < 9; ++q) sv.x[tt * 9 + q] = 0.0;
+                if (sv.act[tt]) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) sv.x[tt * 9 + 6 + c] = A.T[(long long)(3 * k + c) * A.ld + b];
+                }
+            }
+            const long long ld = A.ld;
+            double *oacc = A.acc + b, *oatt = A.att + b, *orat = A.rates + b, *othr = A.thrust + b;
+            sv.extract([=](int k, double ax, double ay, double az, double r0, double r1, double r2, double w0,
+                           double w1, double w2, double th) {
+                oacc[(long long)(3 * k) * ld] = ax;
+                oacc[(long long)(3 * k + 1) * ld] = ay;
+                oacc[(long long)(3 * k + 2) * ld] = az;
+                oatt[(long long)(3 * k) * ld] = r0;
+                oatt[(long long)(3 * k + 1) * ld] = r1;
+                oatt[(long long)(3 * k + 2) * ld] = r2;
+                orat[(long long)(3 * k) * ld] = w0;
+                orat[(long long)(3 * k + 1) * ld] = w1;
+                orat[(long long)(3 * k + 2) * ld] = w2;
+                othr[(long long)k * ld] = th;
+            });
+        }
     }
-#endif
 }
 
 /* the six instantiations of one lane configuration: [gradient_mode][tilt] */
 struct KernelSet {
     const void *fn[3][2];
+    const void *extract_fn[2]; /* [tilt] */
     int lanes, tpl, block, minb;
     int resident; /* blocks per SM the shared-memory carve-out is sized for (default: minb) */
 };
@@ -312,6 +414,8 @@ KernelSet make_kernel_set()
     k.fn[0][0] = (const void *)se3mpc_solve_kernel<LANES, TPL, BLK, MINB, 0, false>;
     k.fn[1][0] = (const void *)se3mpc_solve_kernel<LANES, TPL, BLK, MINB, 1, false>;
     k.fn[2][0] = (const void *)se3mpc_solve_kernel<LANES, TPL, BLK, MINB, 2, false>;
+    k.extract_fn[1] = (const void *)se3mpc_extract_kernel<LANES, TPL, BLK, true>;
+    k.extract_fn[0] = (const void *)se3mpc_extract_kernel<LANES, TPL, BLK, false>;
     k.lanes = LANES;
     k.tpl = TPL;
     k.block = BLK;

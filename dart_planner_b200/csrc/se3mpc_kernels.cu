@@ -57,6 +57,9 @@ KernelChoice g_kernels[] = {
 };
 std::mutex g_mu;
 int g_sms = 0;
+constexpr int QUEUE_SLOTS = 256;
+unsigned long long *g_queue[64] = {nullptr};
+unsigned long long g_queue_next[64] = {0};
 
 int smem_bytes(const KernelChoice &k) { return (k.block / k.lanes) * SM_DOUBLES * (int)sizeof(double); }
 
@@ -214,14 +217,19 @@ static int launch_solve(const dart_se3mpc_params *params, const SolveArgs &a, vo
     SolveArgs args_copy = a;
     void *args[] = {(void *)&P, (void *)&args_copy};
     const long long grid_blocks = grid_for(*k, a.B);
-#if defined(DART_DYNQ)
     {
-        static thread_local unsigned long long *q = nullptr;
-        if (!q && cudaMalloc(&q, 64) != cudaSuccess) return DART_E_CUDA;
-        cudaMemsetAsync(q, 0, 8, (cudaStream_t)cuda_stream);
-        args_copy.queue = q;
+        /* ticket counters of the dynamic schedules: a ring of self-re-arming pairs per device, one
+         * pair per launch in flight (a pair is reused 256 launches later) */
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (!g_queue[dev]) {
+            cudaError_t qe = cudaMalloc(&g_queue[dev], QUEUE_SLOTS * 2 * sizeof(unsigned long long));
+            if (qe == cudaSuccess) qe = cudaMemset(g_queue[dev], 0, QUEUE_SLOTS * 2 * sizeof(unsigned long long));
+            if (qe != cudaSuccess) return set_err(qe, "cudaMalloc(ticket counters)");
+        }
+        args_copy.queue = g_queue[dev] + 2 * (g_queue_next[dev]++ % QUEUE_SLOTS);
     }
-#endif
     const int cold = ((a.x_warm == nullptr || a.no_tilt_promise) && !getenv("DART_SE3MPC_NO_COLD")) ? 0 : 1;
     const void *fn = k->set.fn[params->gradient_mode][cold];
     cudaError_t e = cudaLaunchKernel(fn, dim3((unsigned)grid_blocks), dim3(k->block), args,
@@ -298,9 +306,36 @@ int dart_se3mpc_solve_batch(const dart_se3mpc_params *params, int64_t B, int64_t
                                        0.0, 0.0, nullptr, cuda_stream);
 }
 
+int dart_se3mpc_extract_batch(const dart_se3mpc_params *params, int64_t B, int64_t ld,
+                              const double *thrust_vectors, double *acc, double *att, double *rates,
+                              double *thrust, int32_t untilted, void *cuda_stream)
+{
+    int rc = check_params(params);
+    if (rc) return rc;
+    if (B < 0 || ld < B || !thrust_vectors || !acc || !att || !rates || !thrust) return DART_E_BADARG;
+    if (B == 0) return DART_OK;
+    KernelChoice *k = pick_kernel(params->horizon, 1);
+    rc = prepare(k);
+    if (rc) return rc;
+    dart_se3mpc_params P = *params;
+    ExtractArgs a;
+    a.B = B; a.ld = ld; a.T = thrust_vectors;
+    a.acc = acc; a.att = att; a.rates = rates; a.thrust = thrust;
+    void *args[] = {(void *)&P, (void *)&a};
+    const long long gpb = k->block / k->lanes;
+    long long grid = (B + gpb - 1) / gpb;
+    const long long cap = (long long)g_sms * 8;
+    if (grid > cap) grid = cap;
+    cudaError_t e = cudaLaunchKernel(k->set.extract_fn[untilted ? 0 : 1], dim3((unsigned)grid), dim3(k->block),
+                                     args, 0, (cudaStream_t)cuda_stream);
+    if (e != cudaSuccess) return set_err(e, "cudaLaunchKernel(se3mpc_extract)");
+    g_launches.fetch_add(1);
+    return DART_OK;
+}
+
 int64_t dart_se3mpc_row_stride(const dart_se3mpc_params *params, int32_t row_kind)
 {
-    if (check_params(params) || row_kind < 0 || row_kind > 1) return 0;
+    if (check_params(params) || row_kind < 0 || row_kind > 2) return 0;
     return (int64_t)row_stride_doubles(params->horizon, row_kind);
 }
 
@@ -314,7 +349,7 @@ int dart_se3mpc_solve_batch_rows(const dart_se3mpc_params *params, int64_t B, in
     int rc = check_params(params);
     if (rc) return rc;
     if (B < 0 || ld < B || !p0 || !v0 || !goal || !rows) return DART_E_BADARG;
-    if (row_kind < 0 || row_kind > 1) return DART_E_BADARG;
+    if (row_kind < 0 || row_kind > 2) return DART_E_BADARG;
     if (row_kind == 1 && check_map) return DART_E_UNSUPPORTED; /* controls rows carry no map check */
     const int need = row_stride_doubles(params->horizon, row_kind);
     if (need == 0) return DART_E_UNSUPPORTED; /* the row does not fit its staging block */
@@ -381,6 +416,23 @@ void rows_out(void *dst, const void *src, size_t pitch, size_t B, size_t rows, s
     for (size_t r = 0; r < rows; ++r)
         memcpy((char *)dst + r * B * esz, (const char *)src + r * pitch * esz, B * esz);
 }
+}
+
+void dart_se3mpc_release_thread_workspace(void)
+{
+    if (g_ws.device >= 0) {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        cudaSetDevice(g_ws.device);
+        if (g_ws.stream) cudaStreamSynchronize(g_ws.stream);
+        if (g_ws.stream2) cudaStreamSynchronize(g_ws.stream2);
+        if (g_ws.dev) cudaFree(g_ws.dev);
+        if (g_ws.stream) cudaStreamDestroy(g_ws.stream);
+        if (g_ws.stream2) cudaStreamDestroy(g_ws.stream2);
+        cudaSetDevice(cur);
+    }
+    if (g_ws.pin) cudaFreeHost(g_ws.pin);
+    g_ws = HostWs();
 }
 
 int dart_se3mpc_solve_batch_host(const dart_se3mpc_params *params, int64_t B,
@@ -470,6 +522,12 @@ int dart_se3mpc_solve_batch_host(const dart_se3mpc_params *params, int64_t B,
         }
         const int64_t chunk = 32768;
         int ci = 0;
+        /* on a failure mid-loop the copies already queued still write into the caller's buffers:
+         * wait for them before handing the buffers back */
+        auto drain = [&]() {
+            cudaStreamSynchronize(g_ws.stream);
+            cudaStreamSynchronize(g_ws.stream2);
+        };
         struct HintScope { /* every chunk runs the build chosen for the whole batch */
             explicit HintScope(long long b) { g_batch_hint = b; }
             ~HintScope() { g_batch_hint = 0; }
@@ -481,14 +539,14 @@ int dart_se3mpc_solve_batch_host(const dart_se3mpc_params *params, int64_t B,
     do {                                                                                                     \
         e = cudaMemcpy2DAsync((char *)(dst) + c0 * (esz), Bp * (esz), (const char *)(src) + c0 * (esz),        \
                               (size_t)B * (esz), (size_t)cb * (esz), rows, cudaMemcpyHostToDevice, cs);       \
-        if (e != cudaSuccess) return set_err(e, "cudaMemcpy2DAsync H2D");                                    \
+        if (e != cudaSuccess) return drain(), set_err(e, "cudaMemcpy2DAsync H2D");                           \
     } while (0)
 #define ROWS_D2H(dst, src, rows, esz)                                                                        \
     do {                                                                                                     \
         if (dst) {                                                                                           \
             e = cudaMemcpy2DAsync((char *)(dst) + c0 * (esz), (size_t)B * (esz), (const char *)(src) + c0 * (esz), \
                                   Bp * (esz), (size_t)cb * (esz), rows, cudaMemcpyDeviceToHost, cs);          \
-            if (e != cudaSuccess) return set_err(e, "cudaMemcpy2DAsync D2H");                                \
+            if (e != cudaSuccess) return drain(), set_err(e, "cudaMemcpy2DAsync D2H");                       \
         }                                                                                                    \
     } while (0)
             ROWS_H2D(d_p0, p0, 3, 8);
@@ -503,7 +561,7 @@ int dart_se3mpc_solve_batch_host(const dart_se3mpc_params *params, int64_t B,
                                          status ? d_status + c0 : nullptr, nullptr, acc ? d_acc + c0 : nullptr,
                                          att ? d_att + c0 : nullptr, rates ? d_rates + c0 : nullptr,
                                          thrust ? d_thr + c0 : nullptr, (void *)cs);
-            if (rc) return rc;
+            if (rc) return drain(), rc;
             ROWS_D2H(x_out, d_x, 9 * N, 8);
             ROWS_D2H(cost, d_cost, 1, 8);
             ROWS_D2H(nit, d_nit, 1, 4);

@@ -156,6 +156,9 @@ class ControlsSolution:
         return self.status == 0
 
 
+_DERIVED = ("accelerations", "attitudes", "body_rates", "thrusts")
+
+
 @dataclass
 class HostSolution:
     x: np.ndarray
@@ -169,6 +172,18 @@ class HostSolution:
     body_rates: np.ndarray
     thrusts: np.ndarray
     first_hit: Optional[np.ndarray] = None
+
+    def __getattr__(self, name):
+        # solution rows (from_solution_rows): the derived arrays are not transferred; they are
+        # evaluated from the thrust rows of x on first access (derive.py, :582-654)
+        if name in _DERIVED and "_derive_with" in self.__dict__:
+            from .derive import derive_from_thrust
+            dt, mass, gravity = self.__dict__["_derive_with"]
+            vals = derive_from_thrust(self.thrust_vectors, dt, mass, gravity)
+            for k, v in zip(_DERIVED, vals):
+                self.__dict__[k] = v
+            return self.__dict__[name]
+        raise AttributeError(name)
 
     @staticmethod
     def from_blocks(N: int, out: np.ndarray, meta: np.ndarray) -> "HostSolution":
@@ -202,6 +217,20 @@ class HostSolution:
         include/dart_se3mpc.h): views, no copies."""
         meta = rows[:, 19 * N + 1: 19 * N + 4].view(np.int32)         # (B, 6)
         sol = HostSolution.from_rows(N, rows, meta.T)
+        sol.first_hit = None if (meta[:, 4] == -2).all() else meta[:, 4]
+        return sol
+
+    @staticmethod
+    def from_solution_rows(N: int, rows: np.ndarray, params) -> "HostSolution":
+        """rows: (B, stride) solution rows (DART_ROWS_SOLUTION: x | cost | counters): views, no
+        copies.  accelerations / attitudes / body_rates / thrusts are derived on first access."""
+        meta = rows[:, 9 * N + 1: 9 * N + 4].view(np.int32)           # (B, 6)
+        sol = HostSolution(x=rows[:, : 9 * N], cost=rows[:, 9 * N], nit=meta[:, 0], nfev=meta[:, 1],
+                           status=meta[:, 2], task=meta[:, 3], accelerations=None, attitudes=None,
+                           body_rates=None, thrusts=None)
+        for k in _DERIVED:
+            del sol.__dict__[k]
+        sol.__dict__["_derive_with"] = (float(params.dt), float(params.mass), float(params.gravity))
         sol.first_hit = None if (meta[:, 4] == -2).all() else meta[:, 4]
         return sol
 
@@ -253,7 +282,9 @@ def solve_batch_tensors(params: _cabi.Params, inp, B: int, *, has_goal=None, x_w
     assert inp.dtype == torch.float64 and inp.is_cuda and inp.shape[0] == 9 and inp.is_contiguous()
     assert 0 <= B <= ld
     if out is None:
-        out = torch.empty((out_rows(N), ld), dtype=torch.float64, device=inp.device)
+        # rows the kernel does not write (outputs != "all") must not read as garbage
+        alloc = torch.empty if outputs == "all" else torch.zeros
+        out = alloc((out_rows(N), ld), dtype=torch.float64, device=inp.device)
     if meta is None:
         meta = torch.empty((4, ld), dtype=torch.int32, device=inp.device)
     assert out.shape == (out_rows(N), ld) and out.is_contiguous() and out.dtype == torch.float64
@@ -314,7 +345,10 @@ class BatchWorkspace:
         self.warm_mask = None
         self.grid, self.safety_margin, self.collision_threshold, self.hit = None, 1.0, 0.6, None
         self.h_inp = self.h_out = self.h_meta = self.h_rows = None
-        self.row_kind = 1 if outputs == "controls" else 0      # DART_ROWS_CONTROLS / DART_ROWS_FULL
+        # DART_ROWS_FULL / DART_ROWS_CONTROLS / DART_ROWS_SOLUTION
+        if outputs not in ("all", "controls", "solution"):
+            raise ValueError("outputs must be 'all', 'controls' or 'solution'")
+        self.row_kind = {"all": 0, "controls": 1, "solution": 2}[outputs]
         self.row_stride = int(_cabi.lib().dart_se3mpc_row_stride(C.byref(params), self.row_kind))
         if pinned:
             self.h_inp = torch.zeros((9, self.ld), dtype=torch.float64).pin_memory()
@@ -418,8 +452,10 @@ class BatchWorkspace:
         writes every problem's result row straight into pinned host memory over PCIe (full
         128-byte lines); no copy in either direction.  Returns the pinned (B, stride) row block
         (`HostSolution.from_packed_rows(N, rows.numpy())` gives the named views).  A workspace
-        built with ``outputs="controls"`` gets controls rows: thrust vectors, cost and counters
-        only (`HostSolution.from_control_rows`), a fifth of the bytes."""
+        built with ``outputs="solution"`` gets solution rows (x, cost, counters -- what
+        ``scipy.optimize.minimize`` returns; `HostSolution.from_solution_rows` derives the rest on
+        the host on first access), half the bytes; ``outputs="controls"`` gets controls rows:
+        thrust vectors, cost and counters only (`HostSolution.from_control_rows`), a fifth."""
         torch = _torch()
         if not self.rows_supported:
             raise RuntimeError("row output needs pinned buffers and a horizon of at most 25 steps")
@@ -454,14 +490,44 @@ class BatchWorkspace:
                 ho + (9 * N + 1) * es if derived else None, ho + (12 * N + 1) * es if derived else None,
                 ho + (15 * N + 1) * es if derived else None, ho + (18 * N + 1) * es if derived else None)
         _cabi.check(rc, "dart_se3mpc_solve_batch_host")
+        self.h_meta[3].fill_(-1)      # the host entry returns no task code (status carries the outcome)
         return self.h_out, self.h_meta
 
     def solve_host(self, p0, v0, goal) -> HostSolution:
         self.stage_host_inputs(p0, v0, goal)
         if self.rows_supported and self.B < 65536 and self.outputs == "all":
-            return HostSolution.from_packed_rows(self.N, self.solve_rows().numpy())
+            return HostSolution.from_packed_rows(self.N, self.solve_rows().numpy().copy())
+        if self.rows_supported and self.outputs == "solution":
+            return HostSolution.from_solution_rows(self.N, self.solve_rows().numpy().copy(), self.params)
         h_out, h_meta = self.solve_staged()
         return HostSolution.from_blocks(self.N, h_out.numpy()[:, : self.B], h_meta.numpy()[:, : self.B])
+
+
+def extract_batch(thrust_vectors, config: Optional[SE3MPCConfig] = None, *, mass: float = 1.5,
+                  gravity: float = 9.81, dt: Optional[float] = None, untilted: bool = False):
+    """`_extract_solution_from_result` (se3_mpc_planner.py:582-654) for B thrust sequences on the
+    GPU: (B, N, 3) thrust vectors -> (accelerations, attitudes, body_rates, thrusts) host arrays
+    of the reference's shapes.  The same device code as the solve kernel's epilogue."""
+    torch = _torch()
+    T = np.ascontiguousarray(thrust_vectors, np.float64)
+    B, N, _ = T.shape
+    cfg = config or SE3MPCConfig(prediction_horizon=N)
+    params = make_params(cfg, mass=mass, gravity=gravity, dt=dt)
+    if int(params.horizon) != N:
+        raise ValueError("thrust_vectors must have config.prediction_horizon steps")
+    ld = max(32, (B + 31) // 32 * 32)
+    t_in = torch.zeros((3 * N, ld), dtype=torch.float64, device="cuda")
+    t_in[:, :B] = torch.as_tensor(T.reshape(B, 3 * N)).cuda().t()
+    out = torch.zeros((10 * N, ld), dtype=torch.float64, device="cuda")
+    es = 8 * ld
+    rc = _cabi.lib().dart_se3mpc_extract_batch(
+        C.byref(params), B, ld, t_in.data_ptr(), out.data_ptr(), out.data_ptr() + 3 * N * es,
+        out.data_ptr() + 6 * N * es, out.data_ptr() + 9 * N * es, 1 if untilted else 0,
+        torch.cuda.current_stream().cuda_stream)
+    _cabi.check(rc, "dart_se3mpc_extract_batch")
+    h = out[:, :B].t().contiguous().cpu().numpy()
+    return (h[:, : 3 * N].reshape(B, N, 3), h[:, 3 * N: 6 * N].reshape(B, N, 3),
+            h[:, 6 * N: 9 * N].reshape(B, N, 3), h[:, 9 * N:])
 
 
 def plan_batch(positions, velocities, goals, config: Optional[SE3MPCConfig] = None, *,

@@ -132,6 +132,17 @@ int dart_se3mpc_solve_batch_map(const dart_se3mpc_params *params, int64_t B, int
                                 double margin, double threshold, int32_t *first_hit,
                                 void *cuda_stream);
 
+/* Solution extraction alone: `_extract_solution_from_result` / `_compute_attitudes_and_rates`
+ * (se3_mpc_planner.py:582-654) for B given thrust sequences -- the code the solve kernel's epilogue
+ * runs, callable with arbitrary thrust vectors.  thrust_vectors: SoA rows 3k+c (k = step,
+ * c = x/y/z) of pitch ld; outputs as in dart_se3mpc_solve_batch.  A step with |T| <= 1e-6 gets zero
+ * attitude and rates and does not advance the reference's prev_R (:617, :647-651).
+ * untilted != 0: the caller promises T_x = T_y = 0 at every step (what a cold-started solve
+ * produces); the 7-slot instantiation's extraction runs (closed form when every T_z > 1e-6). */
+int dart_se3mpc_extract_batch(const dart_se3mpc_params *params, int64_t B, int64_t ld,
+                              const double *thrust_vectors, double *acc, double *att, double *rates,
+                              double *thrust, int32_t untilted, void *cuda_stream);
+
 /* Row output: the same solve (and, with check_map != 0, the same fused safety check), with every
  * problem's whole result written as ONE contiguous row -- the arrays the reference packs into
  * the Trajectory it returns for one solve (se3_mpc_planner.py:656-675, from :582-654) next to
@@ -148,10 +159,17 @@ int dart_se3mpc_solve_batch_map(const dart_se3mpc_params *params, int64_t B, int
  *   double [0, 3N) T (rows 6N..9N of x: the thrust vectors, :361-376) | [3N] cost |
  *   the same six int32 (first_hit = -2) -- 3N+4 doubles (256 B instead of 1 280 B at N = 8);
  *   no solution extraction is computed, check_map must be 0.
+ * row_kind 2 (DART_ROWS_SOLUTION): what scipy.optimize.minimize itself returns (:256-268) --
+ *   double [0, 9N) x | [9N] cost | the same six int32 -- 9N+4 doubles (640 B instead of
+ *   1 280 B at N = 8).  The derived arrays of :582-654 (acceleration, attitude, body rate,
+ *   thrust magnitude) are pure functions of the thrust rows of x and dt and are left to the
+ *   caller (dart_planner_b200.planner.HostSolution derives them on first access); the fused
+ *   map check is available.
  * dart_se3mpc_row_stride returns the minimal stride for the row kind, or 0 when this horizon's
  * row does not fit the staging block (full rows: N > 25): use the SoA entries then. */
 #define DART_ROWS_FULL 0
 #define DART_ROWS_CONTROLS 1
+#define DART_ROWS_SOLUTION 2
 int64_t dart_se3mpc_row_stride(const dart_se3mpc_params *params, int32_t row_kind);
 int dart_se3mpc_solve_batch_rows(const dart_se3mpc_params *params, int64_t B, int64_t ld,
                                  const double *p0, const double *v0, const double *goal,
@@ -188,6 +206,11 @@ int dart_se3mpc_solve_batch_host(const dart_se3mpc_params *params, int64_t B,
                                  double *cost_host, int32_t *nit_host, int32_t *nfev_host,
                                  int32_t *status_host, double *acc_host, double *att_host,
                                  double *rates_host, double *thrust_host);
+
+/* Frees what dart_se3mpc_solve_batch_host caches for the CALLING thread (device workspace, mapped
+ * pinned staging block, two streams) after draining them.  A host thread that used the host
+ * entry calls this before it exits; the next call of the host entry allocates again. */
+void dart_se3mpc_release_thread_workspace(void);
 
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t dart_launch_count(void);

@@ -58,3 +58,17 @@ def solve_batch(params, p0, v0, goal, has_goal=None, x_warm=None, grid=None):
     if rc != 0:
         raise RuntimeError(f"emu_solve_batch: {rc}")
     return r
+
+
+def extract_batch(params, T, untilted=False):
+    """The kernel core's solution extraction on (B, N, 3) thrust vectors."""
+    T = np.ascontiguousarray(T, np.float64)
+    B, N, _ = T.shape
+    assert N == params.horizon
+    acc = np.zeros((B, N, 3)); att = np.zeros((B, N, 3)); rates = np.zeros((B, N, 3)); thr = np.zeros((B, N))
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib().emu_extract_batch(C.byref(params), C.c_long(B), vp(T), vp(acc), vp(att), vp(rates), vp(thr),
+                                 C.c_int(1 if untilted else 0))
+    if rc != 0:
+        raise RuntimeError(f"emu_extract_batch: {rc}")
+    return acc, att, rates, thr

@@ -84,3 +84,38 @@ extern "C" int emu_solve_batch(const dart_se3mpc_params *P, long B, const double
     }
     return 0;
 }
+
+/* solution extraction alone (the kernel core's `extract`), T: (B, N, 3) problem-major */
+template <int TPL, bool TILT>
+static void extract_one(const dart_se3mpc_params &P, const double *T, double *acc, double *att,
+                        double *rates, double *thrust)
+{
+    Solver<SeqGroup, TPL, 0, false, TILT> sv(P, nullptr, nullptr, nullptr);
+    const int N = P.horizon;
+    for (int k = 0; k < TPL; ++k)
+        for (int q = 0; q < 9; ++q) sv.x[k * 9 + q] = (k < N && q >= 6) ? T[3 * k + q - 6] : 0.0;
+    sv.extract([&](int k, double ax, double ay, double az, double a0, double a1, double a2,
+                   double w0, double w1, double w2, double th) {
+        acc[3 * k] = ax; acc[3 * k + 1] = ay; acc[3 * k + 2] = az;
+        att[3 * k] = a0; att[3 * k + 1] = a1; att[3 * k + 2] = a2;
+        rates[3 * k] = w0; rates[3 * k + 1] = w1; rates[3 * k + 2] = w2;
+        thrust[k] = th;
+    });
+}
+
+extern "C" int emu_extract_batch(const dart_se3mpc_params *P, long B, const double *T, double *acc,
+                                 double *att, double *rates, double *thrust, int untilted)
+{
+    const int N = P->horizon;
+    if (N < 1 || N > 32) return -2;
+    for (long b = 0; b < B; ++b) {
+        const double *t = T + 3L * N * b;
+        double *a = acc + 3L * N * b, *at = att + 3L * N * b, *r = rates + 3L * N * b, *th = thrust + (long)N * b;
+        if (N <= 8) {
+            if (untilted) extract_one<8, false>(*P, t, a, at, r, th); else extract_one<8, true>(*P, t, a, at, r, th);
+        } else {
+            if (untilted) extract_one<32, false>(*P, t, a, at, r, th); else extract_one<32, true>(*P, t, a, at, r, th);
+        }
+    }
+    return 0;
+}

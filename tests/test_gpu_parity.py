@@ -471,7 +471,8 @@ def test_row_output_limits():
     assert L.dart_se3mpc_row_stride(C.byref(make_params(dp.SE3MPCConfig(prediction_horizon=8))), 0) == 160
     assert L.dart_se3mpc_row_stride(C.byref(make_params(dp.SE3MPCConfig(prediction_horizon=22))), 0) == 432
     assert L.dart_se3mpc_row_stride(C.byref(make_params(dp.SE3MPCConfig(prediction_horizon=8))), 1) == 32
-    assert L.dart_se3mpc_row_stride(C.byref(make_params(dp.SE3MPCConfig(prediction_horizon=8))), 2) == 0
+    assert L.dart_se3mpc_row_stride(C.byref(make_params(dp.SE3MPCConfig(prediction_horizon=8))), 2) == 80
+    assert L.dart_se3mpc_row_stride(C.byref(make_params(dp.SE3MPCConfig(prediction_horizon=8))), 3) == 0
     # the row of a 40-step horizon does not fit the staging block: refused, SoA entries serve it
     pr = make_params(dp.SE3MPCConfig(prediction_horizon=40, dt=0.1))
     assert L.dart_se3mpc_row_stride(C.byref(pr), 0) == 0
@@ -499,7 +500,9 @@ def test_row_output_limits():
     assert call(None, 160) == -1
     assert call(rows.data_ptr(), 32, kind=1) == 0                         # controls rows
     assert call(rows.data_ptr(), 16, kind=1) == -1
-    assert call(rows.data_ptr(), 160, kind=2) == -1
+    assert call(rows.data_ptr(), 80, kind=2) == 0                         # solution rows
+    assert call(rows.data_ptr(), 64, kind=2) == -1
+    assert call(rows.data_ptr(), 160, kind=3) == -1
     assert call(rows.data_ptr(), 32, kind=1, check_map=1) == -2           # no map check in controls rows
     torch.cuda.synchronize()
 
@@ -533,6 +536,53 @@ def test_controls_rows_match_the_full_solution(N, B):
     got_w = HostSolution.from_control_rows(N, ws.solve_rows().numpy())
     np.testing.assert_array_equal(got_w.thrust_vectors, ref_w.thrust_vectors)
     np.testing.assert_array_equal(got_w.nfev, ref_w.nfev)
+
+
+@pytest.mark.parametrize("N,B", [(8, 4096), (6, 333), (4, 50), (13, 200), (40, 64)])
+def test_solution_rows_match_the_full_solution(N, B):
+    """DART_ROWS_SOLUTION: x, cost and counters (what scipy's minimize returns) straight into pinned
+    host memory, half the bytes of a full row; the derived arrays are evaluated on the host from the
+    thrust rows on first access (derive.py restates :582-654).  x / cost / counters: same bits as
+    the resident solve; derived arrays: the tolerances of the fixture tests.  Cold, warm (tilted
+    thrusts, zero-thrust steps) and with the fused map check."""
+    import dart_planner_b200 as dp
+    from dart_planner_b200.config import make_params
+    from dart_planner_b200.planner import BatchWorkspace, HostSolution
+    p0, v0, goal = bench_inputs(300 + N, B, 2.0)
+    pr = make_params(dp.SE3MPCConfig(prediction_horizon=N, dt=0.1, min_thrust=0.0))
+    full = BatchWorkspace(pr, B, pinned=False)
+    full.set_inputs_device(p0, v0, goal)
+    ws = BatchWorkspace(pr, B, pinned=True, outputs="solution")
+    assert ws.rows_supported and ws.row_stride == (9 * N + 4 + 15) // 16 * 16
+    assert ws.d2h_bytes_rows == ws.row_stride * 8 * B
+    ws.stage_host_inputs(p0, v0, goal)
+
+    def check(ref, got):
+        np.testing.assert_array_equal(got.x, ref.x)
+        np.testing.assert_array_equal(got.cost, ref.cost)
+        for f in ("nit", "nfev", "status", "task"):
+            np.testing.assert_array_equal(getattr(got, f), getattr(ref, f), err_msg=f)
+        np.testing.assert_allclose(got.thrusts, ref.thrusts, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(got.accelerations, ref.accelerations, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(got.attitudes, ref.attitudes, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(got.body_rates, ref.body_rates, rtol=0, atol=1e-9)
+
+    check(full.solve_device().numpy(), HostSolution.from_solution_rows(N, ws.solve_rows().numpy(), pr))
+    assert (ws.h_rows.numpy()[:B, 9 * N + 1: 9 * N + 4].view(np.int32)[:, 4] == -2).all()
+    assert (ws.h_rows.numpy()[:B, 9 * N + 4:] == 0).all()
+    rng = np.random.default_rng(N)
+    xw = full.solve_device().numpy().x.copy()
+    xw[:, 6 * N:] += rng.normal(0, 0.8, xw[:, 6 * N:].shape)
+    xw[::5, 6 * N + 3: 6 * N + 6] = 0.0           # a zero thrust that min_thrust = 0 keeps: invalid step
+    grid = dp.DenseOccupancyGrid((128, 128, 128), (-64, -64, -64), 0.4)
+    grid.add_obstacles(rng.uniform(-15, 15, (32, 3)), rng.uniform(0.8, 2.5, 32))
+    for w in (full, ws):
+        w.set_warm(xw)
+        w.set_map(grid, 1.0, 0.6)
+    ref_w = full.solve_device().numpy()
+    got_w = ws.solve_host(p0, v0, goal)
+    check(ref_w, got_w)
+    np.testing.assert_array_equal(got_w.first_hit, ref_w.first_hit)
 
 
 def test_gpu_chaotic_configuration_within_the_oracles_own_sensitivity(oracle_mod):

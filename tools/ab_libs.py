@@ -2,7 +2,7 @@
 """A/B of two builds of the library in ONE process on one box (box-to-box variation is larger than
 most kernel changes): interleaved event-timed launches with an L2 flush, plus 20 launches back to
 back between one event pair (the event tick is ~1 us), and a bit-for-bit comparison of the results.
-usage: python tools/ab_libs.py libA.so libB.so [B list]     (N = 8, bench distribution, seed 1)"""
+usage: python tools/ab_libs.py libA.so libB.so [libC.so ...] [B list]     (N = 8, bench distribution, seed 1)"""
 import ctypes as C, statistics, sys
 sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 import numpy as np, torch
@@ -10,12 +10,14 @@ import dart_planner_b200 as dp
 from dart_planner_b200 import _cabi
 from dart_planner_b200.config import make_params
 libs = {}
-for path in sys.argv[1:3]:
+paths = [a for a in sys.argv[1:] if a.endswith('.so')]
+rest = [a for a in sys.argv[1:] if not a.endswith('.so')]
+for path in paths:
     L = C.CDLL(path)
     vp, i64 = C.c_void_p, C.c_int64
     L.dart_se3mpc_solve_batch.argtypes = [C.POINTER(_cabi.Params), i64, i64] + [vp] * 16 + [vp]
     libs[path] = L
-Bs = [int(b) for b in sys.argv[3].split(",")] if len(sys.argv) > 3 else [4096, 65536, 1 << 20]
+Bs = [int(b) for b in rest[0].split(",")] if rest else [4096, 65536, 1 << 20]
 N = 8
 params = make_params(dp.SE3MPCConfig(prediction_horizon=N, dt=0.1))
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -52,5 +54,5 @@ for B in Bs:
             e.record(stream); torch.cuda.synchronize(); chain.setdefault(k, []).append(a.elapsed_time(e) / 20)
     print("   chained x20: " + " | ".join(f"{k.split('/')[-1]} {statistics.median(v)*1e3:.2f} us" for k, v in chain.items()))
     ks = list(libs)
-    same = bool((outs[ks[0]][0] == outs[ks[1]][0]).all())
+    same = all(bool((outs[ks[0]][0] == outs[k][0]).all()) and bool((outs[ks[0]][1] == outs[k][1]).all()) for k in ks[1:])
     print(f"B={B}: " + " | ".join(f"{k.split('/')[-1]} {statistics.median(v)*1e3:.1f} us ({B/statistics.median(v)/1e3:.1f} M/s)" for k, v in res.items()) + f" identical={same}", flush=True)

@@ -4,7 +4,7 @@ GPU box (tools/ab_libs.py, DART_SE3MPC_LIB=...):
 
   python tools/build_variant.py TAG [-DFOO ...] [--units a.cu,b.cu]
 
-compiles every unit with the extra flags into gpurun_scratch/TAG/ and links
+compiles every unit with the extra flags into /tmp/dart_variant_TAG/ and links
 gpurun_scratch/libdart_TAG.so (git-ignored; travels to the box with the snapshot)."""
 import os
 import subprocess
@@ -19,8 +19,9 @@ from dart_planner_b200 import build as b  # noqa: E402
 def main():
     tag = sys.argv[1]
     extra = [a for a in sys.argv[2:] if not a.startswith("--units")]
-    out = os.path.join(ROOT, "gpurun_scratch", tag)
+    out = os.path.join("/tmp", "dart_variant_" + tag)      # objects stay out of the gpurun snapshot
     os.makedirs(out, exist_ok=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_scratch"), exist_ok=True)
     lib = os.path.join(ROOT, "gpurun_scratch", f"libdart_{tag}.so")
 
     def one(unit):

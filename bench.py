@@ -198,6 +198,105 @@ def workload_config(args):
             "l2": f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)"}
 
 
+def sharded_config_legs(torch, dist, dp, params, world, rank, stream, dt):
+    """BASELINE configs[3] and configs[4] on the `world` GPUs of this launch (all ranks call this):
+    the global batch is cut by problem index, every GPU solves its resident slice, results return
+    through ONE gather.  Device-timed (CUDA events on the launching stream around solve + gather +
+    the copy into host memory on rank 0), max over ranks; strong scaling (the global size is fixed)."""
+    from dart_planner_b200.closed_loop import ClosedLoopSim
+    from dart_planner_b200.sharding import ShardedSolver, shard_range
+
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    out = {}
+    # ---- configs[3]: 1 Mi Monte-Carlo initial states, one goal, seed 3 --------------------------
+    Bg = 1 << 20
+    rng = np.random.default_rng(3)
+    p0 = rng.normal((0, 0, 2), 1.0, (Bg, 3))
+    v0 = rng.normal(0, 0.5, (Bg, 3))
+    goal = np.tile([10.0, 0.0, 5.0], (Bg, 1))
+    lo, hi = shard_range(Bg, world, rank)
+    for outputs in ("solution", "all"):
+        solver = ShardedSolver(params, outputs=outputs)
+        solver.stage(p0[lo:hi], v0[lo:hi], goal[lo:hi], presliced=True, global_B=Bg)
+        for _ in range(2):
+            solver.run()
+        times = []
+        sol = None
+        for _ in range(5):
+            sync_all()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            sol = solver.run()
+            b.record(stream)
+            torch.cuda.synchronize()
+            times.append(max_over_ranks(a.elapsed_time(b)))
+        ms = statistics.mean(times)
+        leg = {"value": Bg / (ms * 1e-3), "unit": UNIT, "ms": ms, "n_gpus": world, "scaling": "strong",
+               "row_bytes": None, "gather": "one NCCL gather of packed rows to rank 0 + one pinned copy per slice"
+               if world > 1 else "single GPU: one pinned copy of the packed rows"}
+        if rank == 0:
+            leg["row_bytes"] = int(solver._pinned.shape[1] * 8)
+            # bit-identity: rank 0 alone solves a sample spread over every shard
+            idx = np.arange(0, Bg, 257)
+            alone = dp.plan_batch(p0[idx], v0[idx], goal[idx], dp.SE3MPCConfig(prediction_horizon=int(params.horizon), dt=dt),
+                                  to_host=True)
+            leg["identical_to_one_gpu_on_sample"] = bool(
+                np.array_equal(sol.x[idx], alone.x) and np.array_equal(sol.cost[idx], alone.cost)
+                and np.array_equal(sol.nfev[idx], alone.nfev) and np.array_equal(sol.status[idx], alone.status))
+            leg["sample"] = int(len(idx))
+            leg["nit_hist"] = np.bincount(sol.nit, minlength=4).tolist()
+        out[f"configs[3] 1 Mi Monte-Carlo solves sharded by problem index, {outputs} rows gathered to rank 0 host memory"] = leg
+        del solver, sol
+    # ---- configs[4]: 65536 drones x 100 replans (10 s at 10 Hz), warm starts, resident state ----
+    Bd = 65536
+    a4, _, c4 = workload_inputs(Bd, 4)
+    b4 = np.random.default_rng(44).uniform(-2, 2, (Bd, 3))
+    lo, hi = shard_range(Bd, world, rank)
+    sim = ClosedLoopSim(params, max(hi - lo, 1), plant_dt=dt)
+    final = torch.empty((world * (Bd // world + 1), 3), dtype=torch.float64, device="cuda") if rank == 0 else None
+
+    def closed_loop():
+        sim.reset(a4[lo:hi], b4[lo:hi], c4[lo:hi])
+        sync_all()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        sim.run(100, stream, track_counters=False)
+        pos = sim.positions().contiguous()
+        if world > 1:       # the only exchange: final positions to rank 0
+            width = Bd // world + 1
+            send = torch.zeros((width, 3), dtype=torch.float64, device="cuda")
+            send[: hi - lo] = pos
+            dist.gather(send, [final[r * width:(r + 1) * width] for r in range(world)] if rank == 0 else None, dst=0)
+        b.record(stream)
+        torch.cuda.synchronize()
+        return max_over_ranks(a.elapsed_time(b)), pos
+
+    closed_loop()
+    cl_ms, pos = closed_loop()
+    leg = {"value": Bd * 100 / (cl_ms * 1e-3), "unit": UNIT, "total_ms": cl_ms, "launches_per_gpu": 100,
+           "n_gpus": world, "scaling": "strong", "drones_per_gpu": int(hi - lo)}
+    if rank == 0 and world > 1:
+        # the first shard's final positions must equal a single-GPU run of the same drones
+        ref = ClosedLoopSim(params, hi - lo, plant_dt=dt)
+        ref.reset(a4[lo:hi], b4[lo:hi], c4[lo:hi])
+        ref.run(100, stream, track_counters=False)
+        leg["shard0_identical_to_standalone"] = bool(torch.equal(ref.positions(), pos)
+                                                     and torch.equal(final[: hi - lo], pos))
+    out["configs[4] closed loop: 65536 drones x 100 replans (10 s at 10 Hz), warm starts, resident state, sharded"] = leg
+    return out
+
+
 def time_steps(torch, fn, flush, steps, warmup, stream):
     """K timed steps, each bracketed by CUDA events on the launching stream, L2 flushed in
     between (outside the event pairs).  Returns summed milliseconds."""
@@ -289,20 +388,30 @@ def main():
     # ---- e2e: pinned host -> device -> solve -> pinned host -------------------------------
     barrier()
     sampler.active.set()
-    # below the chunk-pipelining threshold the kernel itself moves the data: it reads the pinned
-    # input block and writes packed result rows into pinned host memory over PCIe (zero-copy,
-    # BatchWorkspace.solve_rows); from 65536 problems up, chunked copies on two streams
-    use_rows = ws.rows_supported and B < 65536
-    e2e_call = (lambda: ws.solve_rows(stream)) if use_rows else (lambda: ws.solve_staged(stream))
-    ms_e2e = time_steps(torch, e2e_call, flush, args.steps, args.warmup, stream)
-    if use_rows:    # what arrived in host memory is the resident solve's result, bit for bit
-        from dart_planner_b200.planner import HostSolution
-        got = HostSolution.from_packed_rows(N, ws.h_rows.numpy()[:B])
-        dev = ws.solve_device(stream).numpy()
-        e2e_checked = bool(np.array_equal(got.x, dev.x) and np.array_equal(got.nfev, dev.nfev)
-                           and np.array_equal(got.body_rates, dev.body_rates))
+    # The kernel itself moves the data: it reads the pinned input block and writes one packed
+    # result row per problem into pinned host memory over PCIe (zero-copy, BatchWorkspace.solve_rows).
+    # The headline uses SOLUTION rows -- x, cost and the counters, i.e. what scipy's minimize hands
+    # the reference planner (:256-268); the derived arrays of :582-654 are pure functions of the
+    # thrust rows of x and HostSolution evaluates them on first access.  `e2e_full_rows` (below)
+    # is the same call returning them from the device as well (twice the bytes).
+    from dart_planner_b200.planner import HostSolution
+    ws_e2e = BatchWorkspace(params, B, pinned=True, outputs="solution")
+    use_rows = ws_e2e.rows_supported
+    if use_rows:
+        ws_e2e.stage_host_inputs(p0, v0, goal)
+        e2e_call = lambda: ws_e2e.solve_rows(stream)
     else:
-        dev = ws.solve_device(stream).numpy()
+        e2e_call = lambda: ws.solve_staged(stream)
+    ms_e2e = time_steps(torch, e2e_call, flush, args.steps, args.warmup, stream)
+    dev = ws.solve_device(stream).numpy()
+    if use_rows:    # what arrived in host memory is the resident solve's result, bit for bit
+        got = HostSolution.from_solution_rows(N, ws_e2e.h_rows.numpy()[:B], params)
+        e2e_checked = bool(np.array_equal(got.x, dev.x) and np.array_equal(got.cost, dev.cost)
+                           and np.array_equal(got.nfev, dev.nfev) and np.array_equal(got.status, dev.status)
+                           and np.allclose(got.attitudes, dev.attitudes, rtol=0, atol=1e-12)
+                           and np.allclose(got.body_rates, dev.body_rates, rtol=0, atol=1e-9)
+                           and np.allclose(got.thrusts, dev.thrusts, rtol=0, atol=1e-12))
+    else:
         e2e_checked = bool(np.array_equal(ws.h_out.numpy()[: 9 * N, :B].T, dev.x))
     sampler.active.clear()
     barrier()
@@ -310,6 +419,13 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / (float(t.item()) * 1e-3)
+
+    # ---- BASELINE configs[3] / configs[4] on all GPUs of this launch ----------------------------
+    sharded = None
+    if not args.no_extras:
+        sampler.active.set()
+        sharded = sharded_config_legs(torch, dist, dp, params, world, rank, stream, args.dt)
+        sampler.active.clear()
 
     if rank != 0:
         sampler.stop()
@@ -343,16 +459,19 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": ws.h2d_bytes,
-                "d2h_bytes_per_step": ws.d2h_bytes_rows if use_rows else ws.d2h_bytes,
+                "d2h_bytes_per_step": ws_e2e.d2h_bytes_rows if use_rows else ws.d2h_bytes,
                 "ms_per_step": float(sum(ms_e2e)) / args.steps,
-                "api": ("dart_planner_b200.planner.BatchWorkspace.solve_rows (pinned host buffers; the kernel "
-                        "reads them and writes the result rows over PCIe itself, no separate copies)")
+                "api": ("dart_planner_b200.planner.BatchWorkspace(outputs='solution').solve_rows (pinned host "
+                        "buffers; the kernel reads them and writes one row [x | cost | counters] per problem "
+                        "over PCIe itself, no separate copies; derived arrays evaluated lazily on the host)")
                 if use_rows else "dart_planner_b200.planner.BatchWorkspace.solve_staged (pinned host buffers)",
                 "matches_resident_solve": e2e_checked},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "host": {"numa_bound_to_gpu": bool(numa_bound), "cores_visible": len(all_cpus) if all_cpus else None},
     }
+    if sharded is not None:
+        line["sharded_configs"] = sharded
     info = [C.c_int32() for _ in range(5)]
     if L.dart_se3mpc_kernel_info(C.byref(params), B, *[C.byref(i) for i in info]) == 0:
         line["kernel_info"] = {"lanes_per_problem": info[0].value, "block": info[1].value,
@@ -415,16 +534,37 @@ def main():
             sampler.active.set()
             m1 = time_steps(torch, lambda: w2.solve_device(stream), flush, 10, 3, stream)
             m2 = time_steps(torch, lambda: w2.solve_staged(stream), flush, 5, 3, stream)
+            w2s = BatchWorkspace(params, Bs, pinned=True, outputs="solution")
+            w2s.stage_host_inputs(a0, b0, c0)
+            m3 = time_steps(torch, lambda: w2s.solve_rows(stream), flush, 5, 3, stream)
+            rows_ok = bool(np.array_equal(HostSolution.from_solution_rows(N, w2s.h_rows.numpy()[:Bs], params).x[::97],
+                                          w2.solve_device(stream).numpy().x[::97]))
+            del w2s
             sampler.active.clear()
             k_ms = statistics.mean(m1)
             sweep[f"B{Bs}"] = {"value": Bs / (k_ms * 1e-3), "kernel_ms": k_ms,
                                "hbm_frac": alg_bytes_per_solve(N) * Bs / (k_ms * 1e-3) / 1e9 / hbm_peak,
                                "fp64_frac": flops_per_solve * Bs / (k_ms * 1e-3) / 1e12 / fp64_peak,
-                               "e2e_value": Bs / (statistics.mean(m2) * 1e-3)}
+                               "e2e_value": Bs / (statistics.mean(m3) * 1e-3),
+                               "e2e_matches_resident_solve": rows_ok,
+                               "e2e_full_soa_copies_value": Bs / (statistics.mean(m2) * 1e-3)}
             del w2
         line["sweep"] = sweep
+        # end to end with FULL rows: the derived arrays (acceleration, attitude, body rate, thrust
+        # magnitude) computed on the device and transferred too -- 1 280 B instead of 640 B per solve
+        if ws.rows_supported:
+            sampler.active.set()
+            mf = time_steps(torch, lambda: ws.solve_rows(stream), flush, 50, 5, stream)
+            sampler.active.clear()
+            gf = HostSolution.from_packed_rows(N, ws.h_rows.numpy()[:B])
+            line["e2e_full_rows"] = {
+                "value": B / (statistics.mean(mf) * 1e-3), "unit": UNIT, "ms_per_step": statistics.mean(mf),
+                "h2d_bytes_per_step": ws.h2d_bytes, "d2h_bytes_per_step": ws.d2h_bytes_rows,
+                "matches_resident_solve": bool(np.array_equal(gf.x, dev.x) and np.array_equal(gf.body_rates, dev.body_rates)
+                                               and np.array_equal(gf.nfev, dev.nfev)),
+                "api": "BatchWorkspace(outputs='all').solve_rows"}
         # end to end with controls rows (thrust vectors + cost + counters only: what a server that
-        # forwards thrust commands sends back), reported beside `e2e`, which returns whole trajectories
+        # forwards thrust commands sends back)
         wc = BatchWorkspace(params, B, pinned=True, outputs="controls")
         if wc.rows_supported:
             wc.stage_host_inputs(p0, v0, goal)

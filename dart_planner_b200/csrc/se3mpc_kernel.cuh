@@ -53,6 +53,8 @@ struct SolveArgs {
     /* dynamic schedules: queue[0] ticket counter, queue[1] finished blocks; both zero at launch and
      * re-armed by the last block of the launch */
     unsigned long long *queue;
+    /* two-phase schedule: context slots, grid x (2 GPB - 1) x ctx_doubles(1) doubles */
+    double *stash;
 };
 
 /* doubles of one result row (before padding) and the padded stride; 0 when the row does not fit
@@ -97,28 +99,49 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
 #endif
     constexpr int SCHED = (MINB >= 3) ? DART_THROUGHPUT_SCHED : DART_LATENCY_SCHED;
     constexpr bool LOCK = (SCHED == 2) || (SCHED == 3);
+    using SolverT = Solver<SubWarp<LANES>, TPL, GM, (MINB >= 3), TILT>;
+    /* two-phase schedule (SCHED 4): contexts of the problems between their first iteration and
+     * the rest of their solve, GPB - 1 left over + GPB new ones at most, per block, in global
+     * memory (L2-resident: written once, read once) */
+    constexpr int STASH_CAP = 2 * GPB - 1;
+    constexpr int CTXD = SolverT::ctx_doubles(1);
+    __shared__ int s_cont[GPB];
+    __shared__ int s_stash_n;
     /* one problem, solved by this thread's sub-warp.  `alive` = false (lock-step builds only): a
      * padding sub-warp that solves a copy of the last problem and writes nothing, so that every
-     * thread of the block reaches the block barriers */
-    auto solve_one = [&](const long long b, const bool alive) {
+     * thread of the block reaches the block barriers.
+     * phase 0: the whole solve.  Phases of the two-phase schedule, block-uniform: 1 = a fresh
+     * problem's start and FIRST iteration (finished: results out; else its context goes to the
+     * block's stash), 2 = a stashed problem (`alive` = this sub-warp has one, taken from slot
+     * `b_in`) continues to the end, the block in lock step. */
+    auto solve_one = [&](const long long b_in, const bool alive, const int phase) {
         (void)alive;
         bool refused = false;
-        Solver<SubWarp<LANES>, TPL, GM, (MINB >= 3), TILT> sv(P, sm, ws, wy);
+        long long b = b_in;
+        SolverT sv(P, sm, ws, wy);
         if (GM == 2) {
             sv.obs.g = A.grid;
             sv.obs.w = P.w_obstacle;
             sv.obs.free_level = P.obstacle_free_level;
+        }
+        double *stash = nullptr;
+        if constexpr (SCHED == 4) stash = A.stash + (long long)blockIdx.x * STASH_CAP * CTXD;
+        if (phase == 2) {
+            if (alive) b = sv.restore_context(stash + b_in * CTXD, 1);
+            else b = 0;
         }
         double p0[3], v0[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             p0[c] = __ldg(A.p0 + c * A.ld + b);
             v0[c] = __ldg(A.v0 + c * A.ld + b);
-            sv.goal[c] = __ldg(A.goal + c * A.ld + b);
+            if (phase != 2) sv.goal[c] = __ldg(A.goal + c * A.ld + b);
         }
-        sv.has_goal = A.has_goal ? (A.has_goal[b] != 0) : true;
-        const bool warm = A.x_warm != nullptr && (A.warm_mask == nullptr || A.warm_mask[b] != 0);
-        if (warm) {
+        if (phase != 2) sv.has_goal = A.has_goal ? (A.has_goal[b] != 0) : true;
+        const bool warm = phase != 2 && A.x_warm != nullptr && (A.warm_mask == nullptr || A.warm_mask[b] != 0);
+        if (phase == 2) {
+            /* nothing to start */
+        } else if (warm) {
             /* plain loads: in the closed loop x_out aliases x_warm */
             const double *xw = A.x_warm + b;
             const long long ld = A.ld;
@@ -153,13 +176,44 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
             sv.cold_start(p0, v0);
         DP_TICK(0);
         SolveStats st;
-        if constexpr (LOCK) {
+        if constexpr (SCHED == 4) {
+            if (phase == 1) {
+                const bool run = alive && !refused;
+                if (run) {
+                    sv.begin();
+                    if (sv.task == 0) sv.template iterate<true>();
+                }
+                /* unfinished problems go to the stash, packed: slot = count so far + rank among
+                 * this round's continuing sub-warps */
+                const int cont = (run && sv.task == 0) ? 1 : 0;
+                if (sv.grp.leader()) s_cont[gib] = cont;
+                __syncthreads();
+                int pos = s_stash_n, total = 0;
+#pragma unroll
+                for (int j = 0; j < GPB; ++j) {
+                    pos += (j < gib) ? s_cont[j] : 0;
+                    total += s_cont[j];
+                }
+                if (cont) sv.save_context(stash + (long long)pos * CTXD, 1, b);
+                __syncthreads();
+                if (threadIdx.x == 0) s_stash_n += total;
+                if (!run || cont) return;
+            } else {
+                for (;;) {
+                    const int go = (alive && sv.task == 0) ? 1 : 0;
+                    if (!__syncthreads_or(go)) break;
+                    if (go) sv.template iterate<false>();
+                }
+                if (!alive) return;
+            }
+            sv.finish(st);
+        } else if constexpr (LOCK) {
             /* the warps of a block start every iteration together */
             if (!refused) sv.begin();
             for (;;) {
                 const int go = (!refused && sv.task == 0) ? 1 : 0;
                 if (!__syncthreads_or(go)) break;
-                if (go) sv.iterate();
+                if (go) sv.template iterate<false>();
             }
             if (refused || !alive) return;
             sv.finish(st);
@@ -302,7 +356,7 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
             ti = __shfl_sync(0xffffffffu, ti, 0);
             if (ti >= ntasks) break;
             const long long b = ti * PPW + (threadIdx.x & 31) / LANES;
-            if (b < A.B) solve_one(b, true);
+            if (b < A.B) solve_one(b, true, 0);
             __syncwarp();
         }
     } else if constexpr (SCHED == 2) {
@@ -315,7 +369,41 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
             const long long blk = s_ticket;
             if (blk >= rounds) break;
             const long long b = blk * GPB + gib;
-            solve_one(b < A.B ? b : A.B - 1, b < A.B);
+            solve_one(b < A.B ? b : A.B - 1, b < A.B, 0);
+        }
+    } else if constexpr (SCHED == 4) {
+        /* Two-phase schedule.  The solves differ 3x in length (1 to 3 iterations on the bench
+         * mix); run to the end side by side, a sub-warp whose problem stops after the first
+         * iteration idles while its warp finishes the others.  Here a block alternates between
+         *   phase 1: GPB fresh problems (one ticket) through their start and FIRST iteration --
+         *            uniform work, in code specialised for "no stored pair"; the finished ones
+         *            are written out, the others' contexts are stashed;
+         *   phase 2: as soon as GPB contexts are stashed (or no fresh problem is left), GPB of
+         *            them continue to the end, all sub-warps busy from the second iteration on. */
+        __shared__ long long s_ticket;
+        const long long rounds = (A.B + GPB - 1) / GPB;
+        if (threadIdx.x == 0) s_stash_n = 0;
+        bool fresh = true;
+        for (;;) {
+            __syncthreads();
+            const int n = s_stash_n;
+            if (n >= GPB || (!fresh && n > 0)) {
+                const int take = n < GPB ? n : GPB;
+                __syncthreads();
+                if (threadIdx.x == 0) s_stash_n = n - take;
+                solve_one((long long)(n - take + gib), gib < take, 2);
+                continue;
+            }
+            if (!fresh) break;
+            if (threadIdx.x == 0) s_ticket = (long long)atomicAdd(A.queue, 1ull);
+            __syncthreads();
+            const long long blk = s_ticket;
+            if (blk >= rounds) {
+                fresh = false;
+                continue;
+            }
+            const long long b = blk * GPB + gib;
+            solve_one(b < A.B ? b : A.B - 1, b < A.B, 1);
         }
     } else {
         /* block-uniform trip count + a warp barrier per round: the sub-warps of a warp start every
@@ -326,12 +414,12 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
             __syncwarp();
             const long long b = blk * GPB + gib;
             if constexpr (LOCK)
-                solve_one(b < A.B ? b : A.B - 1, b < A.B);
+                solve_one(b < A.B ? b : A.B - 1, b < A.B, 0);
             else if (b < A.B)
-                solve_one(b, true);
+                solve_one(b, true, 0);
         }
     }
-    if constexpr (SCHED == 1 || SCHED == 2) {
+    if constexpr (SCHED == 1 || SCHED == 2 || SCHED == 4) {
         /* the last block to finish re-arms the ticket counter for the next launch that uses it */
         __syncthreads();
         if (threadIdx.x == 0) {

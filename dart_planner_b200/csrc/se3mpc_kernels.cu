@@ -60,6 +60,24 @@ int g_sms = 0;
 constexpr int QUEUE_SLOTS = 256;
 unsigned long long *g_queue[64] = {nullptr};
 unsigned long long g_queue_next[64] = {0};
+/* context stash of the two-phase schedule: a small ring of buffers per device, one per launch in
+ * flight; a launch that reuses a buffer first waits (on its stream) for the launch that used it */
+constexpr int STASH_RING = 4;
+struct StashBuf {
+    double *ptr = nullptr;
+    size_t bytes = 0;
+    cudaEvent_t done = nullptr;
+};
+StashBuf g_stash[64][STASH_RING];
+unsigned g_stash_next[64] = {0};
+
+size_t stash_bytes_for(const KernelChoice &k, long long grid)
+{
+    /* upper bound of Solver::ctx_doubles(1) over the gradient modes (se3mpc_core.cuh) */
+    const size_t S = 9 * (size_t)k.tpl, gpb = (size_t)(k.block / k.lanes);
+    const size_t ctx = 16 + 2 * ((S + 31) / 32) + 7 + (size_t)k.lanes * (4 * S + 3 * k.tpl);
+    return (size_t)grid * (2 * gpb - 1) * ctx * sizeof(double);
+}
 
 int smem_bytes(const KernelChoice &k) { return (k.block / k.lanes) * SM_DOUBLES * (int)sizeof(double); }
 
@@ -217,6 +235,7 @@ static int launch_solve(const dart_se3mpc_params *params, const SolveArgs &a, vo
     SolveArgs args_copy = a;
     void *args[] = {(void *)&P, (void *)&args_copy};
     const long long grid_blocks = grid_for(*k, a.B);
+    cudaEvent_t stash_event = nullptr;
     {
         /* ticket counters of the dynamic schedules: a ring of self-re-arming pairs per device, one
          * pair per launch in flight (a pair is reused 256 launches later) */
@@ -229,12 +248,37 @@ static int launch_solve(const dart_se3mpc_params *params, const SolveArgs &a, vo
             if (qe != cudaSuccess) return set_err(qe, "cudaMalloc(ticket counters)");
         }
         args_copy.queue = g_queue[dev] + 2 * (g_queue_next[dev]++ % QUEUE_SLOTS);
+        if (k->minb >= 3) {
+            StashBuf &sb = g_stash[dev][g_stash_next[dev]++ % STASH_RING];
+            const size_t need = stash_bytes_for(*k, grid_blocks);
+            if (sb.done) {
+                cudaError_t se = cudaStreamWaitEvent((cudaStream_t)cuda_stream, sb.done, 0);
+                if (se != cudaSuccess) return set_err(se, "cudaStreamWaitEvent(stash)");
+            } else {
+                cudaError_t se = cudaEventCreateWithFlags(&sb.done, cudaEventDisableTiming);
+                if (se != cudaSuccess) return set_err(se, "cudaEventCreate(stash)");
+            }
+            if (sb.bytes < need) {
+                if (sb.ptr) {
+                    cudaEventSynchronize(sb.done);
+                    cudaFree(sb.ptr);
+                }
+                sb.ptr = nullptr;
+                sb.bytes = 0;
+                cudaError_t se = cudaMalloc(&sb.ptr, need);
+                if (se != cudaSuccess) return set_err(se, "cudaMalloc(context stash)");
+                sb.bytes = need;
+            }
+            args_copy.stash = sb.ptr;
+            stash_event = sb.done;
+        }
     }
     const int cold = ((a.x_warm == nullptr || a.no_tilt_promise) && !getenv("DART_SE3MPC_NO_COLD")) ? 0 : 1;
     const void *fn = k->set.fn[params->gradient_mode][cold];
     cudaError_t e = cudaLaunchKernel(fn, dim3((unsigned)grid_blocks), dim3(k->block), args,
                                      smem_bytes(*k), (cudaStream_t)cuda_stream);
     if (e != cudaSuccess) return set_err(e, "cudaLaunchKernel(se3mpc_solve)");
+    if (stash_event) cudaEventRecord(stash_event, (cudaStream_t)cuda_stream);
     g_launches.fetch_add(1);
     return DART_OK;
 }

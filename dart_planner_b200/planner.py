@@ -477,6 +477,30 @@ class BatchWorkspace:
             stream.synchronize()
         return self.h_rows[: self.B]
 
+    def solve_rows_device(self, stream=None):
+        """Row output into DEVICE memory from the resident inputs (what `ShardedSolver` gathers:
+        one contiguous row per problem, so a rank's slice is one contiguous block).  Returns the
+        (B, stride) device tensor; asynchronous."""
+        torch = _torch()
+        if self.row_stride <= 0:
+            raise RuntimeError("row output needs a horizon of at most 25 steps (64 for controls rows)")
+        if getattr(self, "d_rows", None) is None:
+            self.d_rows = torch.zeros((self.ld, self.row_stride), dtype=torch.float64, device=self.device)
+        stream = stream or torch.cuda.current_stream(self.device)
+        es = 8 * self.ld
+        di = self.inp.data_ptr()
+        g = self.grid._grid() if self.grid is not None else None
+        with torch.cuda.device(self.device):
+            rc = _cabi.lib().dart_se3mpc_solve_batch_rows(
+                C.byref(self.params), self.B, self.ld, di, di + 3 * es, di + 6 * es,
+                _ptr(self.has_goal), _ptr(self.x_warm), _ptr(self.warm_mask),
+                self.d_rows.data_ptr(), self.row_stride, self.row_kind,
+                C.byref(g) if g is not None else None, float(self.safety_margin),
+                float(self.collision_threshold), 1 if (g is not None and self.row_kind != 1) else 0,
+                stream.cuda_stream)
+        _cabi.check(rc, "dart_se3mpc_solve_batch_rows")
+        return self.d_rows[: self.B]
+
     def _solve_staged_pipelined(self):
         """Large batches: the C host entry splits the batch into chunks on two streams so the
         read-back of one chunk overlaps the solve of the next (pinned buffers: fully async)."""

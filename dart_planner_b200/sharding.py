@@ -57,6 +57,33 @@ def gather_columns(local, counts: List[int], dst: int = 0, group=None):
     return torch.cat([b[:, :c] for b, c in zip(bufs, counts)], dim=1)
 
 
+def gather_row_blocks(local, counts: List[int], dst: int = 0, group=None, recv=None):
+    """Gather problem-major row blocks: every rank holds ``(counts[rank], stride)`` (one contiguous
+    result row per problem); rank `dst` receives them in rank order.  ONE collective, written by
+    NCCL straight into slices of one receive block (no concatenation): returns ``(block, width)``
+    on `dst` -- rank r's rows are ``block[r * width : r * width + counts[r]]`` -- and ``(None,
+    width)`` elsewhere.  Slices are padded to the widest one (NCCL has no gatherv)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    assert len(counts) == world and local.shape[0] == counts[rank]
+    width, stride = max(max(counts), 1), local.shape[1]
+    send = local
+    if local.shape[0] != width:
+        send = torch.zeros((width, stride), dtype=local.dtype, device=local.device)
+        send[: local.shape[0]] = local
+    send = send.contiguous()
+    if rank != dst:
+        dist.gather(send, None, dst=dst, group=group)
+        return None, width
+    if recv is None or tuple(recv.shape) != (world * width, stride) or recv.device != local.device:
+        recv = torch.empty((world * width, stride), dtype=local.dtype, device=local.device)
+    dist.gather(send, [recv[r * width:(r + 1) * width] for r in range(world)], dst=dst, group=group)
+    return recv, width
+
+
 class ShardedSolver:
     """Solve a global batch sharded by problem index; results land on rank `dst`.
 
@@ -64,36 +91,65 @@ class ShardedSolver:
     >>> sol = solver.solve(p0, v0, goal)         # every rank passes the same global arrays (or
     ...                                          # only its slice with ``presliced=True``)
     ``sol`` is a HostSolution on rank `dst`, ``None`` elsewhere.
+
+    Data path on the box: each rank's kernel writes one packed result row per problem into device
+    memory (``outputs``: "all" 19N+4 doubles, "solution" x | cost | counters, "controls" thrust
+    vectors | cost | counters), ONE NCCL gather moves the slices over NVLink into one block on
+    `dst`, ONE copy per rank slice brings it into a cached pinned host block, and the HostSolution
+    is a set of views of that block (valid until the next ``solve``; ``copy=True`` detaches it).
+    ``last_timing`` holds the milliseconds of the stages on `dst`.
     """
 
     def __init__(self, params, *, dst: int = 0, group=None,
-                 solve_fn: Optional[Callable] = None, outputs: str = "all"):
+                 solve_fn: Optional[Callable] = None, outputs: str = "all",
+                 rows_fn: Optional[Callable] = None):
         self.params = params
         self.dst = dst
         self.group = group
         self.outputs = outputs
         self._solve_fn = solve_fn
+        self._rows_fn = rows_fn
         self._ws = None
+        self._recv = None
+        self._pinned = None
+        self.last_timing = {}
 
+    # -- local solves -----------------------------------------------------------------------
     def _solve_local(self, p0, v0, goal):
-        """-> (out (19N+1, b) float64, meta (4, b) int32) torch tensors for the local slice."""
-        if self._solve_fn is not None:
-            return self._solve_fn(self.params, p0, v0, goal)
+        """SoA stand-in path (CPU plumbing tests): (out (19N+1, b), meta (4, b)) torch tensors."""
+        return self._solve_fn(self.params, p0, v0, goal)
+
+    def _workspace(self, b):
         from .planner import BatchWorkspace  # raises without CUDA: no CPU fallback
 
-        b = len(p0)
-        if self._ws is None or self._ws.B != b:
+        if self._ws is None or self._ws.B != max(b, 1):
             self._ws = BatchWorkspace(self.params, max(b, 1), pinned=False, outputs=self.outputs)
-        if b == 0:
-            return self._ws.out[:, :0], self._ws.meta[:, :0]
-        self._ws.set_inputs_device(p0, v0, goal)
-        sol = self._ws.solve_device()
-        return sol.out[:, :b], sol.meta[:, :b]
+        return self._ws
 
-    def solve(self, p0, v0, goal, presliced: bool = False, global_B: Optional[int] = None):
+    def _rows_local(self, p0, v0, goal):
+        """-> (b, stride) tensor of packed result rows for the local slice (device tensor on the box)."""
+        if self._rows_fn is not None:
+            return self._rows_fn(self.params, p0, v0, goal, self.outputs)
+        ws = self._workspace(len(p0))
+        if len(p0):
+            ws.set_inputs_device(p0, v0, goal)
+        return self._rows_resident(len(p0))
+
+    def _rows_resident(self, b):
+        ws = self._workspace(b)
+        rows = ws.solve_rows_device()
+        return rows[:b]             # an empty slice still takes part in the gather
+
+    def rows_supported(self) -> bool:
+        if self._solve_fn is not None:
+            return False
+        if self._rows_fn is not None:
+            return True
+        return self._workspace(1).row_stride > 0
+
+    # -- the call ---------------------------------------------------------------------------
+    def _slice(self, p0, v0, goal, presliced, global_B):
         import torch.distributed as dist
-
-        from .planner import HostSolution
 
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         rank = dist.get_rank(self.group) if dist.is_initialized() else 0
@@ -109,14 +165,108 @@ class ShardedSolver:
             B = len(p0)
             lo, hi = shard_range(B, world, rank)
             p0, v0, goal = p0[lo:hi], v0[lo:hi], goal[lo:hi]
-        out, meta = self._solve_local(p0, v0, goal)
+        return B, world, rank, p0, v0, goal
+
+    def stage(self, p0, v0, goal, presliced: bool = False, global_B: Optional[int] = None):
+        """Upload this rank's slice of the inputs (CUDA path); `run()` then solves the resident
+        slice and gathers -- the split bench.py uses to time the solve + gather on the device."""
+        B, world, rank, p0, v0, goal = self._slice(p0, v0, goal, presliced, global_B)
+        if not self.rows_supported() or self._rows_fn is not None:
+            raise RuntimeError("stage()/run() is the CUDA row path")
+        if len(p0):
+            self._workspace(len(p0)).set_inputs_device(p0, v0, goal)
+        self._staged = (B, world, rank, len(p0))
+
+    def run(self, copy: bool = False):
+        B, world, rank, b = self._staged
+        return self._finish(self._rows_resident(b), B, world, rank, copy, None)
+
+    # -- the call ---------------------------------------------------------------------------
+    def solve(self, p0, v0, goal, presliced: bool = False, global_B: Optional[int] = None,
+              copy: bool = False):
+        import time
+
+        B, world, rank, p0, v0, goal = self._slice(p0, v0, goal, presliced, global_B)
+        N = int(self.params.horizon)
+        if not self.rows_supported():
+            return self._solve_soa(p0, v0, goal, shard_counts(B, world), world, rank, N)
+        t0 = time.perf_counter()
+        return self._finish(self._rows_local(p0, v0, goal), B, world, rank, copy, t0)
+
+    def _finish(self, rows, B, world, rank, copy, t0):
+        """gather -> pinned host block -> HostSolution views.  With t0 (solve()) the stages are
+        timed with host clocks and synchronised in between; run() leaves everything queued on the
+        current stream until the final copy has landed."""
+        import time
+
+        import torch
+
+        from .planner import HostSolution
+
         counts = shard_counts(B, world)
+        N = int(self.params.horizon)
+
+        def sync(t):
+            if t0 is not None and t is not None and t.is_cuda:
+                torch.cuda.synchronize(t.device)
+            return time.perf_counter()
+
+        t1 = sync(rows)
+        if world > 1:
+            block, width = gather_row_blocks(rows, counts, self.dst, self.group, self._recv)
+            self._recv = block
+        else:
+            block, width = rows, max(counts[0], 1)
+        if rank != self.dst:
+            return None
+        t2 = sync(block)
+        stride = block.shape[1]
+        if block.is_cuda:
+            if self._pinned is None or self._pinned.shape[0] < B or self._pinned.shape[1] != stride:
+                self._pinned = torch.empty((max(B, 1), stride), dtype=torch.float64).pin_memory()
+            host = self._pinned[:B]
+            at = 0
+            for r, c in enumerate(counts):      # one contiguous copy per rank slice
+                if c:
+                    host[at:at + c].copy_(block[r * width:r * width + c], non_blocking=True)
+                at += c
+            torch.cuda.current_stream(block.device).synchronize()
+            h = host.numpy()
+        else:
+            h = np.concatenate([block[r * width:r * width + c].numpy() for r, c in enumerate(counts)], axis=0) \
+                if world > 1 else block.numpy()
+        t3 = time.perf_counter()
+        if t0 is not None:
+            self.last_timing = {"solve_ms": (t1 - t0) * 1e3, "gather_ms": (t2 - t1) * 1e3,
+                                "to_host_ms": (t3 - t2) * 1e3, "row_bytes": int(stride * 8), "outputs": self.outputs}
+        if copy:
+            h = h.copy()
+        if self.outputs == "all":
+            return HostSolution.from_packed_rows(N, h)
+        if self.outputs == "solution":
+            return HostSolution.from_solution_rows(N, h, self.params)
+        return HostSolution.from_control_rows(N, h)
+
+    def _solve_soa(self, p0, v0, goal, counts, world, rank, N):
+        """Stand-in / long-horizon path: SoA blocks, two padded gathers (rows do not fit N > 25)."""
+        from .planner import HostSolution
+
+        if self._solve_fn is not None:
+            out, meta = self._solve_local(p0, v0, goal)
+        else:
+            ws = self._workspace(len(p0))
+            b = len(p0)
+            if b:
+                ws.set_inputs_device(p0, v0, goal)
+                sol = ws.solve_device()
+                out, meta = sol.out[:, :b], sol.meta[:, :b]
+            else:
+                out, meta = ws.out[:, :0], ws.meta[:, :0]
         if world > 1:
             out = gather_columns(out, counts, self.dst, self.group)
             meta = gather_columns(meta, counts, self.dst, self.group)
         if rank != self.dst:
             return None
-        N = int(self.params.horizon)
         if out.is_cuda:      # transpose on the device, one contiguous read-back
             return HostSolution.from_rows(N, out.t().contiguous().cpu().numpy(), meta.cpu().numpy())
         return HostSolution.from_blocks(N, out.cpu().numpy(), meta.cpu().numpy())

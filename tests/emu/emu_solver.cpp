@@ -15,8 +15,16 @@ static int g_ls_shared = 0; /* 1: the register-capped build's policies (shared l
                              * state, status bit sets) */
 extern "C" void emu_set_ls_shared(int v) { g_ls_shared = v; }
 
+static int g_two_phase = 0; /* 1: first iteration through iterate<true>, then the context is saved,
+                             * a NEW solver object restores it (fresh shared block and pair storage)
+                             * and finishes -- the two-phase schedule's context switch */
+extern "C" void emu_set_two_phase(int v) { g_two_phase = v; }
+
 static int g_cold_special = 0; /* 1: cold starts run the TILT=false instantiation */
 extern "C" void emu_set_cold_special(int v) { g_cold_special = v; }
+
+template <class SV>
+static void finish_outputs(SV &sv, int N, double *x_out, double *acc, double *att, double *rates, double *thrust);
 
 template <int TPL, int GM, bool LSS, bool TILT>
 static void solve_one(const dart_se3mpc_params &P, const double *p0, const double *v0,
@@ -40,7 +48,36 @@ static void solve_one(const dart_se3mpc_params &P, const double *p0, const doubl
         sv.warm_start(p0, v0, [&](int row) { return xw[row]; });
     else
         sv.cold_start(p0, v0);
-    sv.minimize(st);
+    using ST = Solver<SeqGroup, TPL, GM, LSS, TILT>;
+    double smem2[SM_DOUBLES];
+    static double ws2[MMAX][9 * TPL], wy2[MMAX][9 * TPL];
+    ST sv2(P, smem2, ws2, wy2);
+    if (g_two_phase && LSS) {
+        sv.begin();
+        if (sv.task == 0) sv.template iterate<true>();
+        if (sv.task == 0) {
+            static double ctx[ST::ctx_doubles(1)];
+            for (int i = 0; i < ST::ctx_doubles(1); ++i) ctx[i] = 0.0 / 0.0;
+            for (int i = 0; i < SM_DOUBLES; ++i) smem2[i] = 0.0 / 0.0;
+            for (int j = 0; j < MMAX; ++j)
+                for (int i = 0; i < 9 * TPL; ++i) ws2[j][i] = wy2[j][i] = 0.0 / 0.0;
+            if (sv.col > 1) abort();
+            sv.save_context(ctx, 1, 12345);
+            if (GM == 2) sv2.obs = sv.obs;
+            if (sv2.restore_context(ctx, 1) != 12345) abort();
+            while (sv2.task == 0) sv2.template iterate<false>();
+            sv2.finish(st);
+            return finish_outputs(sv2, N, x_out, acc, att, rates, thrust);
+        }
+        sv.finish(st);
+    } else
+        sv.minimize(st);
+    finish_outputs(sv, N, x_out, acc, att, rates, thrust);
+}
+
+template <class SV>
+static void finish_outputs(SV &sv, int N, double *x_out, double *acc, double *att, double *rates, double *thrust)
+{
     for (int k = 0; k < N; ++k)
         for (int q = 0; q < 9; ++q) x_out[(q / 3) * 3 * N + 3 * k + q % 3] = sv.x[k * 9 + q];
     sv.extract([&](int k, double ax, double ay, double az, double a0, double a1, double a2,

@@ -13,17 +13,22 @@ def _params(d):
     return make_params(cfg)
 
 
-@pytest.fixture(params=[0, 1, 2], ids=["regs", "capped", "cold7"])
+@pytest.fixture(params=[0, 1, 2, 3, 4], ids=["regs", "capped", "cold7", "two-phase", "two-phase-cold7"])
 def policy(request):
     """0: the register-rich build (line-search state and status words in registers);
     1: the register-capped build's policies (shared line-search state, status bit sets);
-    2: cold starts through the 7-slot instantiation (lateral thrust slots skipped)."""
+    2: cold starts through the 7-slot instantiation (lateral thrust slots skipped);
+    3, 4: the throughput builds' two-phase schedule -- first iteration through the "no stored
+       pair" copy of the code, then the context is written to a slot and ANOTHER solver object
+       (NaN-poisoned shared block and pair storage) restores it and finishes the solve."""
     import emu
-    emu.lib().emu_set_ls_shared(1 if request.param == 1 else 0)
-    emu.lib().emu_set_cold_special(1 if request.param == 2 else 0)
+    emu.lib().emu_set_ls_shared(1 if request.param in (1, 3, 4) else 0)
+    emu.lib().emu_set_cold_special(1 if request.param in (2, 4) else 0)
+    emu.lib().emu_set_two_phase(1 if request.param in (3, 4) else 0)
     yield request.param
     emu.lib().emu_set_ls_shared(0)
     emu.lib().emu_set_cold_special(0)
+    emu.lib().emu_set_two_phase(0)
 
 
 @pytest.mark.parametrize("name", SOLVER_FIXTURES)

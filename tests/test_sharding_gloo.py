@@ -45,6 +45,71 @@ def _oracle_solve_fn(params, p0, v0, goal):
     return torch.from_numpy(out), torch.from_numpy(meta)
 
 
+def _oracle_rows_fn(params, p0, v0, goal, outputs):
+    """Stand-in local solve in the product's ROW layouts (include/dart_se3mpc.h: full / solution /
+    controls rows, padded to a multiple of 16 doubles)."""
+    import torch
+    import oracle
+    N = int(params.horizon)
+    b = len(p0)
+    payload = {"all": 19 * N + 4, "solution": 9 * N + 4, "controls": 3 * N + 4}[outputs]
+    stride = (payload + 15) // 16 * 16
+    rows = np.zeros((b, stride))
+    if b:
+        op = oracle.make_params(horizon=N, dt=float(params.dt))
+        r = oracle.solve_batch(op, p0, v0, goal, nthreads=2)
+        if outputs == "controls":
+            rows[:, : 3 * N] = r.x[:, 6 * N:]
+            at = 3 * N
+        else:
+            rows[:, : 9 * N] = r.x
+            at = 9 * N
+        rows[:, at] = r.cost
+        if outputs == "all":
+            rows[:, at + 1: at + 1 + 3 * N] = r.accelerations.reshape(b, 3 * N)
+            rows[:, at + 1 + 3 * N: at + 1 + 6 * N] = r.attitudes.reshape(b, 3 * N)
+            rows[:, at + 1 + 6 * N: at + 1 + 9 * N] = r.body_rates.reshape(b, 3 * N)
+            rows[:, at + 1 + 9 * N: at + 1 + 10 * N] = r.thrusts
+            at += 10 * N
+        meta = rows[:, at + 1: at + 4].view(np.int32)
+        meta[:, 0], meta[:, 1], meta[:, 2], meta[:, 4] = r.nit, r.nfev, r.status, -2
+    return torch.from_numpy(rows)
+
+
+def _rows_worker(rank, world, port, B, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from dart_planner_b200.config import SE3MPCConfig, make_params
+        from dart_planner_b200.sharding import ShardedSolver
+        params = make_params(SE3MPCConfig(prediction_horizon=8, dt=0.1))
+        rng = np.random.default_rng(3)
+        p0 = rng.normal((0, 0, 2), 1.0, (B, 3))
+        v0 = rng.normal(0, 0.5, (B, 3))
+        goal = np.tile([10.0, 0.0, 5.0], (B, 1))
+        res = {}
+        for outputs in ("all", "solution", "controls"):
+            solver = ShardedSolver(params, rows_fn=_oracle_rows_fn, outputs=outputs)
+            sol = solver.solve(p0, v0, goal)
+            sol_again = solver.solve(p0, v0, goal, copy=True)      # reuses the receive block
+            if rank == 0:
+                assert np.array_equal(sol.cost, sol_again.cost) and solver.last_timing["outputs"] == outputs
+                if outputs == "controls":
+                    res[outputs] = (sol.thrust_vectors.copy(), sol.cost.copy(), sol.nfev.copy())
+                else:
+                    res[outputs] = (sol.x.copy(), sol.cost.copy(), sol.nit.copy(), sol.nfev.copy(), sol.status.copy(),
+                                    np.asarray(sol.thrusts).copy(), np.asarray(sol.body_rates).copy())
+            else:
+                assert sol is None
+        if rank == 0:
+            q.put(res)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
 def _worker(rank, world, port, B, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -100,3 +165,34 @@ def test_sharded_solve_gathers_in_problem_order(oracle_mod, world, B):
     assert np.array_equal(x, ref.x) and np.array_equal(cost, ref.cost)
     assert np.array_equal(nit, ref.nit) and np.array_equal(nfev, ref.nfev) and np.array_equal(status, ref.status)
     assert np.array_equal(thrusts, ref.thrusts) and np.array_equal(rates, ref.body_rates)
+
+
+@pytest.mark.parametrize("world,B", [(2, 64), (3, 50), (2, 1)])
+def test_sharded_row_gather_all_row_kinds(oracle_mod, world, B):
+    """The product's data path (one packed row per problem, one gather into one receive block,
+    ragged slices, empty slices) for the three row kinds; the solution rows' derived arrays come
+    from the host-side derivation."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rows_worker, args=(r, world, port, B, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(3)
+    p0 = rng.normal((0, 0, 2), 1.0, (B, 3))
+    v0 = rng.normal(0, 0.5, (B, 3))
+    goal = np.tile([10.0, 0.0, 5.0], (B, 1))
+    ref = oracle_mod.solve_batch(oracle_mod.make_params(horizon=8, dt=0.1), p0, v0, goal, nthreads=2)
+    for kind in ("all", "solution"):
+        x, cost, nit, nfev, status, thrusts, rates = got[kind]
+        assert np.array_equal(x, ref.x) and np.array_equal(cost, ref.cost)
+        assert np.array_equal(nit, ref.nit) and np.array_equal(nfev, ref.nfev) and np.array_equal(status, ref.status)
+        np.testing.assert_allclose(thrusts, ref.thrusts, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(rates, ref.body_rates, rtol=0, atol=1e-9)
+    tv, cost, nfev = got["controls"]
+    assert np.array_equal(tv.reshape(B, -1), ref.x[:, 48:]) and np.array_equal(cost, ref.cost) and np.array_equal(nfev, ref.nfev)

@@ -55,4 +55,9 @@ for B in Bs:
     print("   chained x20: " + " | ".join(f"{k.split('/')[-1]} {statistics.median(v)*1e3:.2f} us" for k, v in chain.items()))
     ks = list(libs)
     same = all(bool((outs[ks[0]][0] == outs[k][0]).all()) and bool((outs[ks[0]][1] == outs[k][1]).all()) for k in ks[1:])
+    for k in ks[1:]:
+        dx = float((outs[ks[0]][0][:72] - outs[k][0][:72]).abs().max())
+        ndiff = int((outs[ks[0]][0][:72] != outs[k][0][:72]).any(dim=0).sum())
+        print(f"   {k.split('/')[-1]} vs {ks[0].split('/')[-1]}: {ndiff} problems differ in x, max |dx| {dx:.2e}, "
+              f"counters equal: {bool((outs[ks[0]][1] == outs[k][1]).all())}")
     print(f"B={B}: " + " | ".join(f"{k.split('/')[-1]} {statistics.median(v)*1e3:.1f} us ({B/statistics.median(v)/1e3:.1f} M/s)" for k, v in res.items()) + f" identical={same}", flush=True)

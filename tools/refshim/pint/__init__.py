@@ -44,6 +44,11 @@ class Quantity(np.ndarray):
     def check(self, dim):
         return True
 
+    # pint's Quantity is hashable (the reference uses Quantities as dataclass field defaults,
+    # planning/global_mission_planner.py:45-55); an ndarray is not
+    def __hash__(self):
+        return id(self)
+
 
 class UnitRegistry:
     Quantity = Quantity

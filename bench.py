@@ -672,6 +672,22 @@ def main():
         others["mapper update_map: 200k rays into a 256^3 grid (ray walk + Bayes apply, incl. host staging of the scan)"] = {
             "value": R / (um_ms * 1e-3), "unit": "rays/s", "total_ms": um_ms, "voxel_visits": upd["updated_voxels"],
             "apply_pass_min_bytes": ncell * 12}
+        # the same scan from device-resident point clouds through the no-sync entry (two launches,
+        # nothing read back): what a scan-rate caller pays
+        d_start = torch.as_tensor(rpos.T.copy(), device="cuda")
+        d_dir = torch.as_tensor(rdir.T.copy(), device="cuda")
+        d_hit = torch.as_tensor(rhit, device="cuda")
+        d_mr = torch.full((R,), 30.0, dtype=torch.float64, device="cuda")
+        for _ in range(2):
+            g2.update_map_soa(d_start, d_dir, d_hit, d_mr, stream)
+        torch.cuda.synchronize()
+        ea.record(stream)
+        g2.update_map_soa(d_start, d_dir, d_hit, d_mr, stream)
+        eb.record(stream)
+        torch.cuda.synchronize()
+        ud_ms = ea.elapsed_time(eb)
+        others["mapper update_map, device-resident scan (update_map_soa: two launches, no host sync)"] = {
+            "value": R / (ud_ms * 1e-3), "unit": "rays/s", "total_ms": ud_ms}
         Q = 1 << 22
         qpos = torch.as_tensor(rngm.uniform(-25, 25, (3, Q)), dtype=torch.float64, device="cuda")
         qout = torch.empty(Q, dtype=torch.float64, device="cuda")

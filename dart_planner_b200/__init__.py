@@ -9,10 +9,13 @@ from .config import SE3MPCConfig, load_planner_config  # noqa: F401
 from .types import DroneState, Trajectory  # noqa: F401
 from .planner import (BatchSolution, SE3MPCPlanner, extract_batch, plan_batch,  # noqa: F401
                       solve_batch_tensors)
-from .mapper import DenseOccupancyGrid  # noqa: F401
+from .mapper import DenseOccupancyGrid, SensorObservation  # noqa: F401
+from .mission import BatchedMissionGoals, SemanticWaypoint  # noqa: F401
+from .wire import SignedEnvelope  # noqa: F401
 from .closed_loop import ClosedLoopSim  # noqa: F401
 from .sharding import ShardedSolver, shard_range  # noqa: F401
 
 __all__ = ["SE3MPCConfig", "load_planner_config", "DroneState", "Trajectory", "SE3MPCPlanner",
-           "BatchSolution", "plan_batch", "extract_batch", "solve_batch_tensors", "DenseOccupancyGrid", "ClosedLoopSim",
+           "BatchSolution", "plan_batch", "extract_batch", "solve_batch_tensors", "DenseOccupancyGrid", "SensorObservation", "ClosedLoopSim",
+           "BatchedMissionGoals", "SemanticWaypoint", "SignedEnvelope",
            "ShardedSolver", "shard_range"]

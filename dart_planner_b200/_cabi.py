@@ -46,6 +46,7 @@ class Grid(C.Structure):
         ("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32),
         ("ox", C.c_int32), ("oy", C.c_int32), ("oz", C.c_int32),
         ("resolution", C.c_double), ("prior", C.c_double), ("occ", C.c_void_p),
+        ("cell_bytes", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -112,7 +113,7 @@ def lib():
     L.dart_map_update_batch.argtypes = [C.POINTER(Grid), vp, vp, i64, i64, vp, vp, vp, vp, C.c_double,
                                         C.c_double, C.c_double, vp, vp]
     L.dart_map_update_batch.restype = C.c_int
-    L.dart_map_add_spheres.argtypes = [C.POINTER(Grid), vp, i32, vp, vp, C.c_float, vp]
+    L.dart_map_add_spheres.argtypes = [C.POINTER(Grid), vp, i32, vp, vp, C.c_double, vp]
     L.dart_map_add_spheres.restype = C.c_int
     L.dart_fp64_probe.argtypes = [i32, C.POINTER(i32), vp, vp]
     L.dart_fp64_probe.restype = C.c_int

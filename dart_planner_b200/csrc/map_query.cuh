@@ -13,11 +13,18 @@ namespace dartb200 {
 
 __device__ __forceinline__ int vox(double p, double res) { return (int)floor(p / res); }
 
+/* cell i of the grid as a double: float32 or float64 storage (dart_grid.cell_bytes) */
+__device__ __forceinline__ double grid_cell(const dart_grid &g, long long i)
+{
+    if (g.cell_bytes == 8) return __ldg(static_cast<const double *>(g.occ) + i);
+    return (double)__ldg(static_cast<const float *>(g.occ) + i);
+}
+
 __device__ __forceinline__ double grid_at(const dart_grid &g, int kx, int ky, int kz)
 {
     const int ix = kx - g.ox, iy = ky - g.oy, iz = kz - g.oz;
     if (ix < 0 || iy < 0 || iz < 0 || ix >= g.nx || iy >= g.ny || iz >= g.nz) return g.prior;
-    return (double)__ldg(g.occ + ((long long)iz * g.ny + iy) * g.nx + ix);
+    return grid_cell(g, ((long long)iz * g.ny + iy) * g.nx + ix);
 }
 
 __device__ __forceinline__ double query(const dart_grid &g, double x, double y, double z)

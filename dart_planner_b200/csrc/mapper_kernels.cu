@@ -178,7 +178,8 @@ __device__ __forceinline__ double bayes_update(double p, double lik)
     return fmin(fmax(p, 0.01), 0.99);
 }
 
-__device__ __forceinline__ void apply_cell(float *occ, unsigned long long *counts, long long i,
+template <class CELL>
+__device__ __forceinline__ void apply_cell(CELL *occ, unsigned long long *counts, long long i,
                                            unsigned long long c, double lik_hit, double lik_miss)
 {
     counts[i] = 0ull; /* leave the scratch zeroed for the next scan */
@@ -199,13 +200,14 @@ __device__ __forceinline__ void apply_cell(float *occ, unsigned long long *count
         if (pn == p) break;
         p = pn;
     }
-    occ[i] = (float)p;
+    occ[i] = (CELL)p;
 }
 
 /* pass 2: a streaming read of the 8-byte counters (four cells = two 16-byte loads per thread and
  * trip, so enough bytes are in flight to cover the HBM latency); untouched cells cost nothing more */
+template <class CELL>
 __global__ void __launch_bounds__(256)
-map_apply_counts_kernel(float *occ, unsigned long long *counts, long long ncell, double lik_hit,
+map_apply_counts_kernel(CELL *occ, unsigned long long *counts, long long ncell, double lik_hit,
                         double lik_miss)
 {
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -228,9 +230,10 @@ map_apply_counts_kernel(float *occ, unsigned long long *counts, long long ncell,
 }
 
 /* add_obstacle: one block per sphere, threads sweep the (2r+1)^3 cube; voxel CORNER distance */
+template <class CELL>
 __global__ void __launch_bounds__(256)
-map_add_spheres_kernel(const __grid_constant__ dart_grid g, float *occ, int nsph,
-                       const double *centers, const double *radii, float value)
+map_add_spheres_kernel(const __grid_constant__ dart_grid g, CELL *occ, int nsph,
+                       const double *centers, const double *radii, CELL value)
 {
     const int sidx = blockIdx.x;
     if (sidx >= nsph) return;
@@ -265,6 +268,7 @@ int check_grid(const dart_grid *g)
 {
     if (!g || !g->occ || g->nx <= 0 || g->ny <= 0 || g->nz <= 0 || !(g->resolution > 0.0))
         return DART_E_BADARG;
+    if (g->cell_bytes != 0 && g->cell_bytes != 4 && g->cell_bytes != 8) return DART_E_BADARG;
     return DART_OK;
 }
 
@@ -310,7 +314,7 @@ int dart_map_trace_ray_batch(double resolution, int64_t B, int64_t ld, const dou
     return DART_OK;
 }
 
-int dart_map_update_batch(const dart_grid *g, float *occ_writable, uint64_t *counts, int64_t B,
+int dart_map_update_batch(const dart_grid *g, void *occ_writable, uint64_t *counts, int64_t B,
                           int64_t ld, const double *start, const double *dir,
                           const double *hit_distance, const double *obs_max_range,
                           double mapper_max_range, double prob_hit, double prob_miss,
@@ -327,19 +331,26 @@ int dart_map_update_batch(const dart_grid *g, float *occ_writable, uint64_t *cou
     dart_count_launch_();
     const long long ncell = (long long)g->nx * g->ny * g->nz;
     /* likelihoods exactly as _bayesian_update forms them (:322-327) */
-    map_apply_counts_kernel<<<grid_blocks(ncell), 256, 0, (cudaStream_t)stream>>>(
-        occ_writable, (unsigned long long *)counts, ncell, prob_hit, 1.0 - prob_miss);
+    if (g->cell_bytes == 8)
+        map_apply_counts_kernel<double><<<grid_blocks(ncell), 256, 0, (cudaStream_t)stream>>>(
+            (double *)occ_writable, (unsigned long long *)counts, ncell, prob_hit, 1.0 - prob_miss);
+    else
+        map_apply_counts_kernel<float><<<grid_blocks(ncell), 256, 0, (cudaStream_t)stream>>>(
+            (float *)occ_writable, (unsigned long long *)counts, ncell, prob_hit, 1.0 - prob_miss);
     if (cudaGetLastError() != cudaSuccess) return DART_E_CUDA;
     dart_count_launch_();
     return DART_OK;
 }
 
-int dart_map_add_spheres(const dart_grid *g, float *occ_writable, int32_t n, const double *centers,
-                         const double *radii, float value, void *stream)
+int dart_map_add_spheres(const dart_grid *g, void *occ_writable, int32_t n, const double *centers,
+                         const double *radii, double value, void *stream)
 {
     if (check_grid(g) || !occ_writable || n < 0 || !centers || !radii) return DART_E_BADARG;
     if (n == 0) return DART_OK;
-    map_add_spheres_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(*g, occ_writable, n, centers, radii, value);
+    if (g->cell_bytes == 8)
+        map_add_spheres_kernel<double><<<n, 256, 0, (cudaStream_t)stream>>>(*g, (double *)occ_writable, n, centers, radii, value);
+    else
+        map_add_spheres_kernel<float><<<n, 256, 0, (cudaStream_t)stream>>>(*g, (float *)occ_writable, n, centers, radii, (float)value);
     if (cudaGetLastError() != cudaSuccess) return DART_E_CUDA;
     dart_count_launch_();
     return DART_OK;

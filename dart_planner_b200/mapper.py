@@ -8,11 +8,23 @@ unknown voxels (:154-169).  Here the map is a dense fp32 grid [nz][ny][nx] resid
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Tuple
+import time
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional, Tuple
 
 import numpy as np
 
 from . import _cabi
+
+
+@dataclass
+class SensorObservation:
+    """One range measurement (explicit_geometric_mapper.py:29-37)."""
+    position: np.ndarray
+    direction: np.ndarray
+    hit_distance: Optional[float]
+    max_range: float
+    timestamp: float = 0.0
 
 
 def _torch():
@@ -26,8 +38,15 @@ def _torch():
 class DenseOccupancyGrid:
     def __init__(self, shape: Tuple[int, int, int] = (256, 256, 256),
                  origin_voxel: Tuple[int, int, int] = (-128, -128, -128),
-                 resolution: float = 0.2, prior: float = 0.5, device=None, max_range: float = 50.0):
+                 resolution: float = 0.2, prior: float = 0.5, device=None, max_range: float = 50.0,
+                 dtype: str = "float32"):
+        """dtype "float32" (default: half the bytes; probabilities carry 1e-7 of rounding, e.g. a
+        single miss reads 0.60000002 instead of the reference's 0.6) or "float64" (the reference's
+        own precision: its voxels hold Python floats)."""
         torch = _torch()
+        if dtype not in ("float32", "float64"):
+            raise ValueError("dtype must be 'float32' or 'float64'")
+        self.dtype = dtype
         self.nx, self.ny, self.nz = (int(s) for s in shape)
         self.origin_voxel = tuple(int(o) for o in origin_voxel)
         self.resolution = float(resolution)
@@ -37,12 +56,13 @@ class DenseOccupancyGrid:
         self.total_observations = 0
         self._counts = None                              # update_map scratch (uint64 per cell)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        self.occ = torch.full((self.nz, self.ny, self.nx), prior, dtype=torch.float32, device=self.device)
+        self.occ = torch.full((self.nz, self.ny, self.nx), prior, device=self.device,
+                              dtype=torch.float64 if dtype == "float64" else torch.float32)
 
     # -- plumbing ------------------------------------------------------------------------
     def _grid(self) -> _cabi.Grid:
         return _cabi.Grid(self.nx, self.ny, self.nz, *self.origin_voxel, self.resolution,
-                          self.prob_prior, self.occ.data_ptr())
+                          self.prob_prior, self.occ.data_ptr(), 8 if self.dtype == "float64" else 4, 0)
 
     def _stream(self, stream):
         torch = _torch()
@@ -121,12 +141,25 @@ class DenseOccupancyGrid:
         idx = int(self.are_trajectories_safe(np.asarray(positions, float)[None], safety_margin, threshold)[0])
         return idx < 0, idx
 
-    def update_map(self, positions, directions, hit_distances, max_ranges=50.0, stream=None):
-        """Batched `update_map` (:100-152) for one scan: B observations given as arrays
-        (SensorObservation.position / direction / hit_distance / max_range; hit_distance None or
+    def update_map(self, positions, directions=None, hit_distances=None, max_ranges=50.0, stream=None,
+                   sync: bool = True):
+        """Batched `update_map` (:100-152) for one scan.  Either the reference's argument -- a list
+        of SensorObservation (position / direction / hit_distance / max_range; hit_distance None
+        = no return) -- or the same as arrays / device tensors ((B,3), (B,3), (B,), scalar or (B,);
         NaN = no return).  Two launches: ray walk with per-voxel visit counters, then the Bayes
-        rule applied per voxel.  Returns the reference's counters dict."""
+        rule applied per voxel.  Returns the reference's counters dict; with ``sync=False`` nothing
+        is read back (no host synchronisation: the counters stay device tensors, `total_voxels`
+        is left out), which is what a scan-rate caller with device-resident point clouds uses."""
         torch = _torch()
+        if directions is None:      # the reference's signature: update_map(observations)
+            obs = list(positions)
+            if not obs:
+                return {"updated_voxels": 0, "observations_processed": 0,
+                        "total_voxels": int((self.occ != self.prob_prior).sum().item())}
+            positions = np.array([np.asarray(o.position, np.float64) for o in obs])
+            directions = np.array([np.asarray(o.direction, np.float64) for o in obs])
+            hit_distances = np.array([np.nan if o.hit_distance is None else float(o.hit_distance) for o in obs])
+            max_ranges = np.array([float(o.max_range) for o in obs])
         start = self._soa(positions, 3)
         d = self._soa(directions, 3)
         B = start.shape[1]
@@ -137,19 +170,85 @@ class DenseOccupancyGrid:
             if hd.dtype == object:      # the reference's Optional[float] per observation: None = no return
                 hd = np.array([np.nan if h is None else float(h) for h in hd.reshape(-1)])
             hit_t = torch.as_tensor(np.ascontiguousarray(hd, np.float64).reshape(-1)).to(self.device)
-        mr = torch.as_tensor(np.broadcast_to(np.asarray(max_ranges, np.float64), (B,)).copy()).to(self.device)
-        if self._counts is None:
-            self._counts = torch.zeros(self.nx * self.ny * self.nz, dtype=torch.int64, device=self.device)
-        updated = torch.zeros(1, dtype=torch.int64, device=self.device)
-        g = self._grid()
-        rc = _cabi.lib().dart_map_update_batch(
-            C.byref(g), self.occ.data_ptr(), self._counts.data_ptr(), B, B, start.data_ptr(), d.data_ptr(),
-            hit_t.data_ptr(), mr.data_ptr(), self.max_range, self.prob_hit, self.prob_miss,
-            updated.data_ptr(), self._stream(stream))
-        _cabi.check(rc, "dart_map_update_batch")
+        if torch.is_tensor(max_ranges):
+            mr = max_ranges.to(self.device, torch.float64).reshape(-1).expand(B).contiguous()
+        else:
+            mr = torch.as_tensor(np.broadcast_to(np.asarray(max_ranges, np.float64), (B,)).copy()).to(self.device)
+        updated = self.update_map_soa(start, d, hit_t, mr, stream)
         self.total_observations += B
+        self.last_update_time = time.time()
+        if not sync:
+            return {"updated_voxels": updated, "observations_processed": B}
         return {"updated_voxels": int(updated.item()), "observations_processed": B,
                 "total_voxels": int((self.occ != self.prob_prior).sum().item())}
+
+    def update_map_soa(self, start_soa, dir_soa, hit, max_ranges, stream=None):
+        """Lowest level: (3, B) float64 device tensors (rows x/y/z), (B,) hit distances (NaN = no
+        return) and (B,) per-observation max ranges, all resident.  Two launches, no allocation
+        after the first call, no synchronisation; returns the device counter of voxel visits."""
+        torch = _torch()
+        B = start_soa.shape[1]
+        for t in (start_soa, dir_soa, hit, max_ranges):
+            assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
+        if self._counts is None:
+            self._counts = torch.zeros(self.nx * self.ny * self.nz, dtype=torch.int64, device=self.device)
+            self._updated = torch.zeros(1, dtype=torch.int64, device=self.device)
+        s = stream or torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(s):
+            self._updated.zero_()
+        g = self._grid()
+        rc = _cabi.lib().dart_map_update_batch(
+            C.byref(g), self.occ.data_ptr(), self._counts.data_ptr(), B, B, start_soa.data_ptr(), dir_soa.data_ptr(),
+            hit.data_ptr(), max_ranges.data_ptr(), self.max_range, self.prob_hit, self.prob_miss,
+            self._updated.data_ptr(), s.cuda_stream)
+        _cabi.check(rc, "dart_map_update_batch")
+        return self._updated
+
+    def simulate_lidar_scan(self, drone_state, num_rays: int = 360) -> List[SensorObservation]:
+        """The reference's test scan (:365-397): `num_rays` horizontal rays from the drone, each
+        with a 10 % chance of a return at U(2, 20) m (NumPy's global generator, as there)."""
+        observations = []
+        for i in range(num_rays):
+            angle = 2 * np.pi * i / num_rays
+            direction = np.array([np.cos(angle), np.sin(angle), 0.0])
+            hit_distance = np.random.uniform(2.0, 20.0) if np.random.random() < 0.1 else None
+            observations.append(SensorObservation(position=np.asarray(drone_state.position, np.float64),
+                                                  direction=direction, hit_distance=hit_distance,
+                                                  max_range=self.max_range, timestamp=time.time()))
+        return observations
+
+    def get_local_occupancy_grid(self, center, size: float = 20.0) -> Tuple[np.ndarray, np.ndarray]:
+        """:221-248: a cube of `int(size / resolution)`^3 sample points around `center`
+        (`linspace` per axis, NumPy's meshgrid order) and their occupancies ->
+        (positions (n, n, n, 3), occupancy (n, n, n)) host arrays; the occupancies are one batched
+        query on the device."""
+        center = np.asarray(getattr(center, "magnitude", center), np.float64).reshape(3)
+        half = size / 2
+        lo, hi = center - half, center + half
+        n = int(size / self.resolution)
+        x, y, z = (np.linspace(lo[c], hi[c], n) for c in range(3))
+        pts = np.array(np.meshgrid(x, y, z)).T.reshape(-1, 3)
+        occ = self.query_occupancy_batch(pts).cpu().numpy()
+        return pts.reshape(n, n, n, 3), occ.reshape(n, n, n)
+
+    def occupied_spheres(self, center, size: float = 20.0, threshold: float = 0.6, max_spheres: int = 20,
+                         radius: float = 1.0) -> List[Tuple[np.ndarray, float]]:
+        """The mapper -> planner bridge of the reference's cloud node
+        (cloud/main_improved_threelayer.py:381-398): occupied sample points of the local grid
+        (occupancy > threshold), every `len // max_spheres`-th one becomes a sphere obstacle."""
+        grid, occ = self.get_local_occupancy_grid(center, size)
+        pts = grid[occ > threshold]
+        if pts.size == 0:
+            return []
+        step = max(1, pts.shape[0] // max_spheres)
+        return [(p.copy(), float(radius)) for p in pts[::step]]
+
+    def get_mapping_stats(self) -> Dict[str, Any]:
+        """:353-363 (total_voxels = cells that left the prior)"""
+        nvox = int((self.occ != self.prob_prior).sum().item())
+        return {"total_voxels": nvox, "total_observations": self.total_observations,
+                "memory_efficiency": f"{self.occ.numel() * 4} bytes", "last_update": getattr(self, "last_update_time", 0.0),
+                "resolution": self.resolution, "max_range": self.max_range}
 
     def trace_rays(self, starts, directions, distances, max_vox: int = 0, stream=None):
         """_trace_ray (:250-309) for B rays.  Returns (count (B,) int32, voxels (max_vox,3,B) int32

@@ -653,6 +653,16 @@ class SE3MPCPlanner:
     def clear_obstacles(self) -> None:
         self.obstacles.clear()
 
+    def refresh_obstacles_from_mapper(self, mapper, center, size: float = 20.0, threshold: float = 0.6,
+                                      max_spheres: int = 20, radius: float = 1.0) -> int:
+        """The cloud node's mapper -> planner bridge (cloud/main_improved_threelayer.py:381-398):
+        replace the obstacle list by spheres on the occupied sample points of the mapper's local
+        grid.  Returns the number of spheres."""
+        self.clear_obstacles()
+        for c, r in mapper.occupied_spheres(center, size, threshold, max_spheres, radius):
+            self.add_obstacle(c, r)
+        return len(self.obstacles)
+
     def sense(self, current_state: DroneState, goal_position):
         goal = np.array(to_si(goal_position, "m"), dtype=np.float64).reshape(3)
         if self.goal_position is None or np.linalg.norm(self.goal_position - goal) > 0.5:

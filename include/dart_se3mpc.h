@@ -77,14 +77,18 @@ int dart_ddiv_selftest(int64_t n, uint64_t seed, int32_t emax, uint64_t *mismatc
                        void *cuda_stream);
 
 /* ---- occupancy grid (perception/explicit_geometric_mapper.py) on a dense device grid ----
- * occ: float32 [nz][ny][nx] (x fastest); voxel key (kx,ky,kz) = floor(p/res) lives at index
- * (kx-ox, ky-oy, kz-oz); keys outside the grid read `prior` (the reference's dict miss, :168). */
+ * occ: [nz][ny][nx] (x fastest) of float32 (cell_bytes 4 or 0: half the bytes, probabilities to
+ * 1e-7) or float64 (cell_bytes 8: the reference's own precision -- its voxels hold Python floats);
+ * voxel key (kx,ky,kz) = floor(p/res) lives at index (kx-ox, ky-oy, kz-oz); keys outside the grid
+ * read `prior` (the reference's dict miss, :168). */
 typedef struct dart_grid {
     int32_t nx, ny, nz;
     int32_t ox, oy, oz;
     double resolution;
     double prior;
-    const float *occ;
+    const void *occ;
+    int32_t cell_bytes;
+    int32_t reserved;
 } dart_grid;
 
 int dart_abi_version(void);
@@ -247,15 +251,15 @@ int dart_map_trace_ray_batch(double resolution, int64_t B, int64_t ld, const dou
  * [0.01, 0.99].  counts: caller-owned scratch of nx*ny*nz uint64, zero on entry, zero on return.
  * updated_voxels: optional device counter, incremented by the number of voxel visits (the
  * reference's `updated_voxels`).  Voxels outside the dense grid are visited but not stored. */
-int dart_map_update_batch(const dart_grid *g, float *occ_writable, uint64_t *counts, int64_t B,
+int dart_map_update_batch(const dart_grid *g, void *occ_writable, uint64_t *counts, int64_t B,
                           int64_t ld, const double *start, const double *dir,
                           const double *hit_distance, const double *obs_max_range,
                           double mapper_max_range, double prob_hit, double prob_miss,
                           uint64_t *updated_voxels, void *cuda_stream);
 /* add_obstacle (:399-423): rasterise n spheres (centres [3][n], radii [n]) into a writable
  * grid with the reference's voxel-corner distance test; value 0.9. */
-int dart_map_add_spheres(const dart_grid *g, float *occ_writable, int32_t n,
-                         const double *centers, const double *radii, float value,
+int dart_map_add_spheres(const dart_grid *g, void *occ_writable, int32_t n,
+                         const double *centers, const double *radii, double value,
                          void *cuda_stream);
 
 #ifdef __cplusplus

@@ -113,6 +113,40 @@ def gen_mission():
     print("wrote mission.npz")
 
 
+def gen_local_grid():
+    """get_local_occupancy_grid (:221-248) and the cloud node's occupied-point -> sphere selection
+    (cloud/main_improved_threelayer.py:381-398) on a map built by add_obstacle + two update_map
+    scans of the reference mapper."""
+    from dart_planner.perception.explicit_geometric_mapper import ExplicitGeometricMapper, SensorObservation
+    rng = np.random.default_rng(21)
+    mp = ExplicitGeometricMapper(resolution=0.5, max_range=40.0)
+    cs = np.array([[4.0, 1.0, 2.5], [-3.0, -2.0, 1.0], [1.0, 5.0, 4.0]])
+    rs = np.array([1.5, 1.0, 2.0])
+    for c, r in zip(cs, rs):
+        mp.add_obstacle(c, float(r))
+    R = 400
+    pos = np.tile([0.2, 0.3, 2.0], (R, 1)) + rng.normal(0, 0.05, (R, 3))
+    ang = rng.uniform(0, 2 * np.pi, R)
+    dirs = np.stack([np.cos(ang), np.sin(ang), rng.normal(0, 0.2, R)], axis=1)
+    hit = rng.uniform(2.0, 20.0, R)
+    hit[rng.random(R) < 0.7] = np.nan
+    obs = [SensorObservation(position=pos[i], direction=dirs[i], hit_distance=None if np.isnan(hit[i]) else float(hit[i]),
+                             max_range=40.0, timestamp=0.0) for i in range(R)]
+    mp.update_map(obs[:200])
+    mp.update_map(obs[200:])
+    center, size = np.array([1.3, -0.7, 2.1]), 15.0
+    grid, occ = mp.get_local_occupancy_grid(center, size)
+    pts = grid[occ > 0.6]
+    step = max(1, pts.shape[0] // 20)
+    np.savez_compressed(os.path.join(OUT, "local_grid.npz"), res=np.float64(0.5), max_range=np.float64(40.0),
+                        sph_c=cs, sph_r=rs, pos=pos, dir=dirs, hit=hit, center=center, size=np.float64(size),
+                        occ=occ, grid_corner=grid[0, 0, 0], grid_last=grid[-1, -1, -1], grid_sample=grid[3, 7, 11],
+                        n_occupied=np.int64(pts.shape[0]), spheres=pts[::step])
+    print("wrote local_grid.npz", occ.shape, "occupied", pts.shape[0], "spheres", pts[::step].shape[0],
+          "values", np.unique(np.round(occ, 6))[:8])
+
+
 if __name__ == "__main__":
     gen_wire()
     gen_mission()
+    gen_local_grid()

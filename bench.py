@@ -537,8 +537,13 @@ def main():
             w2s = BatchWorkspace(params, Bs, pinned=True, outputs="solution")
             w2s.stage_host_inputs(a0, b0, c0)
             m3 = time_steps(torch, lambda: w2s.solve_rows(stream), flush, 5, 3, stream)
-            rows_ok = bool(np.array_equal(HostSolution.from_solution_rows(N, w2s.h_rows.numpy()[:Bs], params).x[::97],
-                                          w2.solve_device(stream).numpy().x[::97]))
+            # rows come from the latency build, the resident solve at this size from the throughput
+            # build: same counters, x equal to rounding (a few products are contracted differently
+            # in the exact-size code copies; tools/variant_diff.py) -- compared as such
+            hs = HostSolution.from_solution_rows(N, w2s.h_rows.numpy()[:Bs], params)
+            dv = w2.solve_device(stream).numpy()
+            rows_ok = bool(np.array_equal(hs.nfev[::97], dv.nfev[::97]) and np.array_equal(hs.status[::97], dv.status[::97])
+                           and float(np.abs(hs.x[::97] - dv.x[::97]).max()) < 1e-12)
             del w2s
             sampler.active.clear()
             k_ms = statistics.mean(m1)

@@ -76,5 +76,36 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+# Diagnostic twin of the library for the parity A/B (tests/test_gpu_parity_sweep.py): the N <= 8
+# instantiations compiled with -DDART_NO_CLOSED_FORM (the published breakpoint walk also when no
+# pair is stored), everything else shared with the product build.  Never loaded by the product.
+NOCF_LIB = os.path.join(LIBDIR, "libdart_se3mpc_nocf.so")
+NOCF_UNITS = ["se3mpc_inst_l8.cu", "se3mpc_inst_l8_occ3.cu", "se3mpc_inst_l4.cu"]
+
+
+def build_nocf() -> str:
+    build()
+    os.makedirs(OBJDIR, exist_ok=True)
+
+    def one(unit):
+        src = os.path.join(CSRC, unit)
+        obj = os.path.join(OBJDIR, unit.replace(".cu", ".nocf.o"))
+        if _stale(obj, [src] + HEADERS):
+            r = subprocess.run([nvcc()] + ARCH + COMMON + ["-DDART_NO_CLOSED_FORM", "-c", src, "-o", obj],
+                               capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(f"nvcc failed for {unit} (nocf):\n{r.stderr}")
+        return obj
+
+    with ThreadPoolExecutor(len(NOCF_UNITS)) as ex:
+        special = list(ex.map(one, NOCF_UNITS))
+    objs = [os.path.join(OBJDIR, u.replace(".cu", ".o")) for u in UNITS if u not in NOCF_UNITS] + special
+    if _stale(NOCF_LIB, objs):
+        r = subprocess.run([nvcc()] + ARCH + ["-shared", "-o", NOCF_LIB] + objs, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed (nocf):\n{r.stderr}")
+    return NOCF_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -159,6 +159,7 @@ int check_params(const dart_se3mpc_params *p)
     if (p->max_iterations < 0 || p->max_linesearch < 0) return DART_E_BADARG;
     if (p->gradient_mode < 0 || p->gradient_mode > 2) return DART_E_UNSUPPORTED;
     if (!(p->dt > 0.0) || !(p->mass > 0.0)) return DART_E_BADARG;
+    if (!(p->gtol >= 0.0)) return DART_E_BADARG; /* the Cauchy step relies on it (se3mpc_core.cuh) */
     return DART_OK;
 }
 

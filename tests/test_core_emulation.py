@@ -66,6 +66,27 @@ def _penalty_world(oracle_mod, seed=7):
     return og
 
 
+@pytest.mark.parametrize("N", [3, 5, 6, 8, 13])
+def test_core_projected_gradient_stop_with_unused_slots(oracle_mod, policy, N):
+    """A start on the stationary point of the reference's gradient stops at [401] with nit 0 also
+    when the horizon leaves timestep slots of the lane group unused (their T_z slot holds 0, below
+    min_thrust, and must not enter the projected-gradient norm)."""
+    import emu
+    from dart_planner_b200.config import SE3MPCConfig, make_params
+    rng = np.random.default_rng(60 + N)
+    B = 40
+    goal = np.concatenate([rng.uniform(-15, 15, (B, 2)), rng.uniform(3, 8, (B, 1))], axis=1)
+    xw = np.zeros((B, 9 * N))
+    xw[:, :3 * N] = np.tile(goal, (1, N)) + rng.normal(0, 1e-5, (B, 3 * N))
+    xw[:, 6 * N + 2::3] = 0.5
+    v0 = np.zeros_like(goal)
+    ref = oracle_mod.solve_batch(oracle_mod.make_params(horizon=N, dt=0.1), goal, v0, goal, x_warm=xw, nthreads=4)
+    got = emu.solve_batch(make_params(SE3MPCConfig(prediction_horizon=N, dt=0.1)), goal, v0, goal, x_warm=xw)
+    assert (ref.task == 1).all() and (ref.nit == 0).all()
+    assert (got.nit == ref.nit).all() and (got.nfev == ref.nfev).all() and (got.status == ref.status).all()
+    np.testing.assert_allclose(got.x, ref.x, atol=1e-12)
+
+
 def test_core_grid_penalty_mode_matches_oracle(oracle_mod):
     """gradient_mode 2 (extension, self-oracle): reference gradient + occupancy-grid penalty."""
     import emu

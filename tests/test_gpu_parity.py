@@ -99,6 +99,32 @@ def test_gpu_near_goal_regime(oracle_mod):
     _compare(sol, ref, min_counter_agreement=0.97)
 
 
+def _stationary_warm_starts(rng, N, B, min_thrust=0.5):
+    """Warm starts that sit (almost) on the stationary point of the reference's gradient: P = goal,
+    V = 0, T = (0, 0, min_thrust) -- the projected gradient is ~0, the solve stops at [401]."""
+    goal = np.concatenate([rng.uniform(-15, 15, (B, 2)), rng.uniform(3, 8, (B, 1))], axis=1)
+    xw = np.zeros((B, 9 * N))
+    xw[:, :3 * N] = np.tile(goal, (1, N)) + rng.normal(0, 1e-5, (B, 3 * N))
+    xw[:, 6 * N + 2::3] = min_thrust
+    return goal, xw
+
+
+@pytest.mark.parametrize("N", [3, 5, 6, 8, 13, 20])
+def test_gpu_projected_gradient_stop_with_unused_lanes(oracle_mod, N):
+    """Horizons that leave lanes (or timestep slots) of the group unused: the phantom T_z slots hold
+    0, outside [min_thrust, max_thrust], and must not enter the projected-gradient norm (round-1
+    kernel: they did, so a [401] stop was never taken at N = 5, 6, 7, ...)."""
+    import dart_planner_b200 as dp
+    rng = np.random.default_rng(60 + N)
+    goal, xw = _stationary_warm_starts(rng, N, 300)
+    v0 = np.zeros_like(goal)
+    ref = oracle_mod.solve_batch(oracle_mod.make_params(horizon=N, dt=0.1), goal, v0, goal, x_warm=xw, nthreads=16)
+    assert (ref.task == 1).all() and (ref.nit == 0).all()       # CONV_PGTOL at the start
+    sol = dp.plan_batch(goal, v0, goal, dp.SE3MPCConfig(prediction_horizon=N, dt=0.1), x_warm=xw, to_host=True)
+    _compare(sol, ref)
+    assert (sol.nit == 0).all()
+
+
 def test_gpu_warm_start_and_masks(oracle_mod):
     import dart_planner_b200 as dp
     p0, v0, goal = bench_inputs(22, 2048, 2.0)

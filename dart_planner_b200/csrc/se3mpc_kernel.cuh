@@ -339,9 +339,12 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
             const double dt = A.plant_dt, dt2 = DP_MUL(dt, dt);
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
+                /* the state is read again here (plain loads: p_next / v_next may alias p0 / v0)
+                 * instead of being kept in 12 registers through the whole solve */
+                const double pc = A.p0[c * A.ld + b], vc = A.v0[c * A.ld + b];
                 const double a = DP_ADD(ddiv(sv.x[6 + c], P.mass), c == 2 ? -P.gravity : -0.0);
-                A.p_next[c * A.ld + b] = DP_ADD(DP_ADD(p0[c], DP_MUL(v0[c], dt)), DP_MUL(DP_MUL(0.5, a), dt2));
-                A.v_next[c * A.ld + b] = DP_ADD(v0[c], DP_MUL(a, dt));
+                A.p_next[c * A.ld + b] = DP_ADD(DP_ADD(pc, DP_MUL(vc, dt)), DP_MUL(DP_MUL(0.5, a), dt2));
+                A.v_next[c * A.ld + b] = DP_ADD(vc, DP_MUL(a, dt));
             }
         }
         DP_TICK(41);

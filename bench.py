@@ -31,6 +31,8 @@ sys.path.insert(0, ROOT)
 METRIC = "batched SE(3)-MPC solves/sec"
 UNIT = "solves/s"
 L2_FLUSH_BYTES = 256 << 20
+L2_BYTES = 126 << 20
+E2E_DEPTH = 3
 
 
 def workload_inputs(B, seed):
@@ -195,7 +197,10 @@ def workload_config(args):
             "batch_per_gpu": args.batch, "horizon": args.horizon, "dt": args.dt,
             "max_iterations": 15, "convergence_tolerance": 0.05, "gradient": "reference (:552-580)",
             "parallelism": f"dp{args.gpus} by problem index, replicated params, no collective in the solve",
-            "l2": f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)"}
+            "l2": "value: inputs larger than L2 -- the launches cycle through resident input/output sets "
+                  f"totalling > 2 x {L2_BYTES >> 20} MiB; per_launch_flushed and e2e_single_step: L2 flushed "
+                  f"between timed steps ({L2_FLUSH_BYTES >> 20} MiB write); e2e: inputs and results live in "
+                  "pinned host memory (nothing resident is re-read)"}
 
 
 def sharded_config_legs(torch, dist, dp, params, world, rank, stream, dt):
@@ -371,19 +376,51 @@ def main():
     sampler.start()
 
     # ---- value: kernel on resident inputs ------------------------------------------------
+    # The workload as a planning server sees it: a stream of batches.  K launches queued back to
+    # back between ONE pair of events on the launching stream, cycling through enough resident
+    # input/output sets (each holding the named workload) that a set has left the L2 long before
+    # it comes round again -- the timing rules' "inputs larger than L2" instead of a flush kernel
+    # between launches, whose own tail and the event pair around every 30 us launch are what rank
+    # jitter at N > 1 used to come from.  The per-launch, L2-flushed figure is reported beside it
+    # (`per_launch_flushed`).
+    per_set = B * (9 + 19 * N + 1) * 8 + 4 * B * 4
+    nsets = max(4, -(-2 * L2_BYTES // per_set))
+    ring = []
+    for i in range(nsets):
+        w = BatchWorkspace(params, B, pinned=False, outputs="all")
+        w.set_inputs_device(p0, v0, goal)
+        ring.append(w)
+    for i in range(max(args.warmup, nsets)):
+        ring[i % nsets].solve_device(stream)
     barrier()
     n0 = L.dart_launch_count()
     sampler.active.set()
-    ms = time_steps(torch, lambda: ws.solve_device(stream), flush, args.steps, args.warmup, stream)
+    torch.cuda._sleep(2_000_000)         # ~1 ms of device-side wait: the K launches are queued behind it
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        ring[i % nsets].solve_device(stream)
+    e1.record(stream)
+    torch.cuda.synchronize()
     sampler.active.clear()
-    launches = L.dart_launch_count() - n0 - args.warmup
+    launches = L.dart_launch_count() - n0
     barrier()
-    total_ms = float(sum(ms))
+    total_ms = float(e0.elapsed_time(e1))
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms_max = float(t.item())
     value = world * B * args.steps / (total_ms_max * 1e-3)
+    del ring
+    # the same launch, one event pair per launch, L2 flushed in between (round-1 definition of `value`)
+    barrier()
+    sampler.active.set()
+    ms = time_steps(torch, lambda: ws.solve_device(stream), flush, min(args.steps, 50), args.warmup, stream)
+    sampler.active.clear()
+    tf_ = torch.tensor([float(sum(ms))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tf_, op=dist.ReduceOp.MAX)
+    flushed_value = world * B * len(ms) / (float(tf_.item()) * 1e-3)
 
     # ---- e2e: pinned host -> device -> solve -> pinned host -------------------------------
     barrier()
@@ -402,23 +439,64 @@ def main():
         e2e_call = lambda: ws_e2e.solve_rows(stream)
     else:
         e2e_call = lambda: ws.solve_staged(stream)
-    ms_e2e = time_steps(torch, e2e_call, flush, args.steps, args.warmup, stream)
+    ms_e2e = time_steps(torch, e2e_call, flush, min(args.steps, 50), args.warmup, stream)   # one step at a time
+    # The headline: the same call as a stream of steps, E2E_DEPTH of them in flight (one workspace
+    # + stream each, `solve_rows(wait=False)`): the row write-back of one step (2.6 MB over PCIe)
+    # overlaps the solve of the next.  Every step reads its inputs from pinned host memory and
+    # leaves its result rows in pinned host memory inside the timed region (start event before the
+    # first launch, end event after the last stream has drained).
+    slots = [ws_e2e]
+    streams = [stream]
+    if use_rows:
+        for _ in range(E2E_DEPTH - 1):
+            w = BatchWorkspace(params, B, pinned=True, outputs="solution")
+            w.stage_host_inputs(p0, v0, goal)
+            slots.append(w)
+            streams.append(torch.cuda.Stream())
+        for i in range(max(args.warmup, 2 * len(slots))):
+            slots[i % len(slots)].solve_rows(streams[i % len(slots)], wait=False)
+        torch.cuda.synchronize()
+        for w in slots:
+            w.h_rows.zero_()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda._sleep(2_000_000)
+        s0.record(stream)
+        for st in streams[1:]:
+            st.wait_event(s0)
+        for i in range(args.steps):
+            slots[i % len(slots)].solve_rows(streams[i % len(slots)], wait=False)
+        for st in streams[1:]:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            stream.wait_event(ev)
+        s1.record(stream)
+        torch.cuda.synchronize()
+        e2e_stream_ms = float(s0.elapsed_time(s1))
+    else:
+        e2e_stream_ms = float(sum(ms_e2e)) * args.steps / len(ms_e2e)
     dev = ws.solve_device(stream).numpy()
     if use_rows:    # what arrived in host memory is the resident solve's result, bit for bit
         got = HostSolution.from_solution_rows(N, ws_e2e.h_rows.numpy()[:B], params)
-        e2e_checked = bool(np.array_equal(got.x, dev.x) and np.array_equal(got.cost, dev.cost)
-                           and np.array_equal(got.nfev, dev.nfev) and np.array_equal(got.status, dev.status)
-                           and np.allclose(got.attitudes, dev.attitudes, rtol=0, atol=1e-12)
-                           and np.allclose(got.body_rates, dev.body_rates, rtol=0, atol=1e-9)
-                           and np.allclose(got.thrusts, dev.thrusts, rtol=0, atol=1e-12))
+        e2e_checked = True
+        for w in slots:     # every slot's host block holds the resident solve's result
+            got = HostSolution.from_solution_rows(N, w.h_rows.numpy()[:B], params)
+            e2e_checked = e2e_checked and bool(
+                np.array_equal(got.x, dev.x) and np.array_equal(got.cost, dev.cost)
+                and np.array_equal(got.nfev, dev.nfev) and np.array_equal(got.status, dev.status)
+                and np.allclose(got.attitudes, dev.attitudes, rtol=0, atol=1e-12)
+                and np.allclose(got.body_rates, dev.body_rates, rtol=0, atol=1e-9)
+                and np.allclose(got.thrusts, dev.thrusts, rtol=0, atol=1e-12))
     else:
         e2e_checked = bool(np.array_equal(ws.h_out.numpy()[: 9 * N, :B].T, dev.x))
     sampler.active.clear()
     barrier()
-    t = torch.tensor([float(sum(ms_e2e))], dtype=torch.float64, device="cuda")
+    t = torch.tensor([e2e_stream_ms, float(sum(ms_e2e))], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * args.steps / (float(t.item()) * 1e-3)
+    e2e_value = world * B * args.steps / (float(t[0].item()) * 1e-3)
+    e2e_single_value = world * B * len(ms_e2e) / (float(t[1].item()) * 1e-3)
+    del slots[1:]
 
     # ---- BASELINE configs[3] / configs[4] on all GPUs of this launch ----------------------------
     sharded = None
@@ -436,7 +514,7 @@ def main():
 
     # ---- roofline of the solve kernel (rank 0) ----------------------------------------------
     hbm_peak, peak_src = load_peaks()
-    kernel_ms = statistics.mean(ms)
+    kernel_ms = total_ms / args.steps      # rank 0's own average launch duration in the timed region of `value`
     ab = alg_bytes_per_solve(N) * B
     achieved_gbs = ab / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
@@ -448,8 +526,26 @@ def main():
         try:
             with open(traffic_file) as fh:
                 tf = json.load(fh)
-            roofline["traffic"] = tf.get(f"B{B}_N{N}", {}).get("dram_bytes_per_launch")
+            ent = tf.get(f"B{B}_N{N}", {})
+            roofline["traffic"] = ent.get("dram_bytes_per_launch")
             roofline["traffic_source"] = tf.get("source")
+            if ent.get("warp_inst_per_launch"):
+                # issue roofline: executed warp instructions per launch (ncu count of the same
+                # launch) over the live kernel time, against 4 issue slots per SM per clock
+                props = torch.cuda.get_device_properties(0)
+                clk = (statistics.median(sampler.samples) if sampler.samples else (sampler.max_mhz or 1965)) * 1e6
+                peak_issue = props.multi_processor_count * 4 * clk
+                ach_issue = ent["warp_inst_per_launch"] / (kernel_ms * 1e-3)
+                roofline["issue"] = {
+                    "warp_inst_per_solve": ent["warp_inst_per_launch"] / B, "achieved": ach_issue / 1e9,
+                    "peak": peak_issue / 1e9, "unit": "G warp-inst/s", "frac": ach_issue / peak_issue,
+                    "ipc_per_sm": ach_issue / (props.multi_processor_count * clk),
+                    "fp64_pipe_active_pct_under_ncu": ent.get("fp64_pipe_active_pct"),
+                    "issue_active_pct_under_ncu": ent.get("issue_active_pct"),
+                    "note": "the kernel is bound by instruction issue / dependent-chain latency, not by HBM or "
+                            "FP64 flops: at this instruction count a full issue rate would be "
+                            f"{peak_issue / (ent['warp_inst_per_launch'] / B) / 1e6:.0f} M solves/s per GPU "
+                            "(DESIGN.md section 4, 'Where the ceiling is')"}
         except Exception:
             pass
 
@@ -460,12 +556,19 @@ def main():
         "config": workload_config(args),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": ws.h2d_bytes,
                 "d2h_bytes_per_step": ws_e2e.d2h_bytes_rows if use_rows else ws.d2h_bytes,
-                "ms_per_step": float(sum(ms_e2e)) / args.steps,
-                "api": ("dart_planner_b200.planner.BatchWorkspace(outputs='solution').solve_rows (pinned host "
-                        "buffers; the kernel reads them and writes one row [x | cost | counters] per problem "
-                        "over PCIe itself, no separate copies; derived arrays evaluated lazily on the host)")
+                "ms_per_step": e2e_stream_ms / args.steps, "steps_in_flight": E2E_DEPTH if use_rows else 1,
+                "api": ("dart_planner_b200.planner.BatchWorkspace(outputs='solution').solve_rows(wait=False) "
+                        f"on {E2E_DEPTH} workspaces / streams in rotation (pinned host buffers; the kernel reads "
+                        "them and writes one row [x | cost | counters] per problem over PCIe itself, no separate "
+                        "copies; derived arrays evaluated lazily on the host)")
                 if use_rows else "dart_planner_b200.planner.BatchWorkspace.solve_staged (pinned host buffers)",
                 "matches_resident_solve": e2e_checked},
+        "e2e_single_step": {"value": e2e_single_value, "unit": UNIT, "ms_per_step": float(sum(ms_e2e)) / len(ms_e2e),
+                            "note": "the same call, one step at a time (launch, wait, next): the latency of a step, "
+                                    "not the throughput of a stream of steps"},
+        "per_launch_flushed": {"value": flushed_value, "unit": UNIT, "ms_per_step": float(sum(ms)) / len(ms),
+                               "note": "one event pair per launch, L2 flushed before every launch (cold "
+                                       "instruction and data caches): round 1's definition of `value`"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "host": {"numa_bound_to_gpu": bool(numa_bound), "cores_visible": len(all_cpus) if all_cpus else None},
@@ -585,35 +688,6 @@ def main():
                                                and np.array_equal(gc.nfev, dev.nfev)),
                 "api": "BatchWorkspace(outputs='controls').solve_rows"}
         del wc
-        # the same workload as a stream of batches: launches queued back to back between ONE pair of
-        # events (no per-launch event/launch gap), cycling through enough resident input/output sets
-        # that a set has left the L2 before it comes round again (reported beside `value`, which
-        # keeps the per-launch events + L2 flush of the timing rules)
-        per_set = B * (9 + 19 * N + 1) * 8 + 4 * B * 4
-        nsets = max(2, -(-2 * 126 * (1 << 20) // per_set))
-        ring = []
-        for i in range(nsets):
-            w = BatchWorkspace(params, B, pinned=False, outputs="all")
-            w.set_inputs_device(p0, v0, goal)       # the named workload in every set
-            ring.append(w)
-        for w in ring:
-            w.solve_device(stream)
-        torch.cuda.synchronize()
-        k_chain = 4 * nsets
-        torch.cuda._sleep(2_000_000)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for i in range(k_chain):
-            ring[i % nsets].solve_device(stream)
-        e1.record(stream)
-        torch.cuda.synchronize()
-        chain_ms = e0.elapsed_time(e1) / k_chain
-        line["back_to_back"] = {"value": B / (chain_ms * 1e-3), "unit": UNIT, "ms_per_step": chain_ms,
-                                "launches": k_chain, "resident_sets": nsets,
-                                "working_set_mb": nsets * per_set / 1e6,
-                                "note": "one event pair around the whole stream of launches; inputs rotate "
-                                        "through a working set larger than the L2"}
-        del ring
         # the other BASELINE configs, timed once each (kernel-only, resident inputs); their
         # parity lives in tests/test_gpu_config3.py and tests/test_gpu_closed_loop.py
         others = {}

@@ -7,8 +7,12 @@
  * NumPy's separate multiply/add.
  *
  * These are gather kernels (HBM/L2 latency bound): one thread per query / trajectory / ray,
- * batch-major SoA inputs so a warp's loads of each coordinate row are coalesced; the grid
- * itself (<= 64 MiB at 256^3 fp32) stays L2-resident on B200 (126 MB L2).
+ * batch-major SoA inputs so a warp's loads of each coordinate row are coalesced.  The grid
+ * (64 MiB at 256^3 fp32) fits the 126 MB L2, but a query kernel also streams its own inputs and
+ * outputs through it (32 B per query, as many sectors as the gathers) and the first touch of every
+ * grid sector misses: one cold launch of 4 Mi random queries measures 24 % L2 hits under ncu
+ * (which flushes the caches before the launch) -- about half of the gathers hit, none of the
+ * streamed sectors; profiles/README.md, round 2.
  */
 #include <cuda_runtime.h>
 #include <math.h>

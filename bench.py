@@ -33,6 +33,7 @@ UNIT = "solves/s"
 L2_FLUSH_BYTES = 256 << 20
 L2_BYTES = 126 << 20
 E2E_DEPTH = 3
+VALUE_DEPTH = 4
 
 
 def workload_inputs(B, seed):
@@ -197,6 +198,7 @@ def workload_config(args):
             "batch_per_gpu": args.batch, "horizon": args.horizon, "dt": args.dt,
             "max_iterations": 15, "convergence_tolerance": 0.05, "gradient": "reference (:552-580)",
             "parallelism": f"dp{args.gpus} by problem index, replicated params, no collective in the solve",
+            "steps_in_flight": VALUE_DEPTH,
             "l2": "value: inputs larger than L2 -- the launches cycle through resident input/output sets "
                   f"totalling > 2 x {L2_BYTES >> 20} MiB; per_launch_flushed and e2e_single_step: L2 flushed "
                   f"between timed steps ({L2_FLUSH_BYTES >> 20} MiB write); e2e: inputs and results live in "
@@ -376,8 +378,8 @@ def main():
     sampler.start()
 
     # ---- value: kernel on resident inputs ------------------------------------------------
-    # The workload as a planning server sees it: a stream of batches.  K launches queued back to
-    # back between ONE pair of events on the launching stream, cycling through enough resident
+    # The workload as a planning server sees it: a stream of batches.  K launches queued
+    # between ONE pair of events on the launching stream, cycling through enough resident
     # input/output sets (each holding the named workload) that a set has left the L2 long before
     # it comes round again -- the timing rules' "inputs larger than L2" instead of a flush kernel
     # between launches, whose own tail and the event pair around every 30 us launch are what rank
@@ -390,27 +392,54 @@ def main():
         w = BatchWorkspace(params, B, pinned=False, outputs="all")
         w.set_inputs_device(p0, v0, goal)
         ring.append(w)
-    for i in range(max(args.warmup, nsets)):
-        ring[i % nsets].solve_device(stream)
-    barrier()
-    n0 = L.dart_launch_count()
+    def run_stream(depth, hint):
+        """K steps, `depth` of them in flight (one stream each, round robin); one event pair around
+        all of them on the launching stream.  Returns (milliseconds, launches)."""
+        streams = [stream] + [torch.cuda.Stream() for _ in range(depth - 1)]
+        L.dart_se3mpc_set_inflight_hint(hint)
+        try:
+            for i in range(max(args.warmup, nsets)):
+                ring[i % nsets].solve_device(streams[i % depth])
+            barrier()
+            n0 = L.dart_launch_count()
+            torch.cuda._sleep(2_000_000)     # ~1 ms of device-side wait: the K launches are queued behind it
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for st in streams[1:]:
+                st.wait_event(e0)
+            for i in range(args.steps):
+                ring[i % nsets].solve_device(streams[i % depth])
+            for st in streams[1:]:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                stream.wait_event(ev)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            return float(e0.elapsed_time(e1)), L.dart_launch_count() - n0
+        finally:
+            L.dart_se3mpc_set_inflight_hint(0)
+
+    def max_over_ranks(x):
+        tt = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    # `value`: VALUE_DEPTH steps in flight -- the batches of a stream are independent, so a server
+    # keeps several on the machine at once; the library is told (dart_se3mpc_set_inflight_hint) and
+    # runs them in the throughput build.  `single_stream`: the same K steps strictly one after the
+    # other on one stream (latency build).
     sampler.active.set()
-    torch.cuda._sleep(2_000_000)         # ~1 ms of device-side wait: the K launches are queued behind it
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for i in range(args.steps):
-        ring[i % nsets].solve_device(stream)
-    e1.record(stream)
-    torch.cuda.synchronize()
+    total_ms, launches = run_stream(VALUE_DEPTH, VALUE_DEPTH * B)
     sampler.active.clear()
-    launches = L.dart_launch_count() - n0
     barrier()
-    total_ms = float(e0.elapsed_time(e1))
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
+    total_ms_max = max_over_ranks(total_ms)
     value = world * B * args.steps / (total_ms_max * 1e-3)
+    sampler.active.set()
+    single_ms, _ = run_stream(1, 0)
+    sampler.active.clear()
+    barrier()
+    single_value = world * B * args.steps / (max_over_ranks(single_ms) * 1e-3)
     del ring
     # the same launch, one event pair per launch, L2 flushed in between (round-1 definition of `value`)
     barrier()
@@ -514,7 +543,7 @@ def main():
 
     # ---- roofline of the solve kernel (rank 0) ----------------------------------------------
     hbm_peak, peak_src = load_peaks()
-    kernel_ms = total_ms / args.steps      # rank 0's own average launch duration in the timed region of `value`
+    kernel_ms = total_ms / args.steps      # rank 0's timed region of `value` per launch (launches overlap: the throughput-equivalent duration)
     ab = alg_bytes_per_solve(N) * B
     achieved_gbs = ab / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
@@ -529,6 +558,11 @@ def main():
             ent = tf.get(f"B{B}_N{N}", {})
             roofline["traffic"] = ent.get("dram_bytes_per_launch")
             roofline["traffic_source"] = tf.get("source")
+            # the steps in flight run in the throughput build: its per-solve instruction count is the
+            # one ncu measured on the 65 536-problem launch of the same build
+            thr = tf.get(f"B65536_N{N}", {})
+            if VALUE_DEPTH > 1 and thr.get("warp_inst_per_solve"):
+                ent = dict(thr, warp_inst_per_launch=thr["warp_inst_per_solve"] * B)
             if ent.get("warp_inst_per_launch"):
                 # issue roofline: executed warp instructions per launch (ncu count of the same
                 # launch) over the live kernel time, against 4 issue slots per SM per clock
@@ -566,6 +600,8 @@ def main():
         "e2e_single_step": {"value": e2e_single_value, "unit": UNIT, "ms_per_step": float(sum(ms_e2e)) / len(ms_e2e),
                             "note": "the same call, one step at a time (launch, wait, next): the latency of a step, "
                                     "not the throughput of a stream of steps"},
+        "single_stream": {"value": single_value, "unit": UNIT, "ms_per_step": single_ms / args.steps,
+                          "note": "the same K steps strictly one after the other on one stream (latency build)"},
         "per_launch_flushed": {"value": flushed_value, "unit": UNIT, "ms_per_step": float(sum(ms)) / len(ms),
                                "note": "one event pair per launch, L2 flushed before every launch (cold "
                                        "instruction and data caches): round 1's definition of `value`"},
@@ -576,7 +612,10 @@ def main():
     if sharded is not None:
         line["sharded_configs"] = sharded
     info = [C.c_int32() for _ in range(5)]
-    if L.dart_se3mpc_kernel_info(C.byref(params), B, *[C.byref(i) for i in info]) == 0:
+    L.dart_se3mpc_set_inflight_hint(VALUE_DEPTH * B)      # the build the timed region of `value` ran
+    rc_info = L.dart_se3mpc_kernel_info(C.byref(params), B, *[C.byref(i) for i in info])
+    L.dart_se3mpc_set_inflight_hint(0)
+    if rc_info == 0:
         line["kernel_info"] = {"lanes_per_problem": info[0].value, "block": info[1].value,
                                "grid": info[2].value, "smem_bytes": info[3].value,
                                "regs_per_thread": info[4].value}

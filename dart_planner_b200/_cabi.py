@@ -54,7 +54,7 @@ EXPORTS = [
     "dart_abi_version", "dart_last_cuda_error", "dart_se3mpc_default_params",
     "dart_se3mpc_solve_batch", "dart_se3mpc_solve_batch_map", "dart_se3mpc_closed_loop_step",
     "dart_se3mpc_solve_batch_host", "dart_se3mpc_release_thread_workspace", "dart_se3mpc_row_stride", "dart_se3mpc_solve_batch_rows", "dart_se3mpc_extract_batch",
-    "dart_launch_count",
+    "dart_launch_count", "dart_se3mpc_set_inflight_hint",
     "dart_se3mpc_kernel_info", "dart_map_query_batch", "dart_map_traj_safe_batch",
     "dart_map_trace_ray_batch", "dart_map_update_batch", "dart_map_add_spheres", "dart_fp64_probe", "dart_ddiv_selftest",
 ]
@@ -101,6 +101,8 @@ def lib():
                                                [C.POINTER(Grid), C.c_double, C.c_double, i32, vp])
     L.dart_se3mpc_solve_batch_rows.restype = C.c_int
     L.dart_launch_count.restype = C.c_int64
+    L.dart_se3mpc_set_inflight_hint.argtypes = [i64]
+    L.dart_se3mpc_set_inflight_hint.restype = C.c_int
     L.dart_se3mpc_kernel_info.argtypes = [C.POINTER(Params), i64] + [C.POINTER(i32)] * 5
     L.dart_se3mpc_kernel_info.restype = C.c_int
     L.dart_map_query_batch.argtypes = [C.POINTER(Grid), i64, i64, vp, vp, vp]

@@ -90,9 +90,13 @@ int set_err(cudaError_t e, const char *what)
 thread_local long long g_batch_hint = 0; /* > 0: choose the build for this many problems (the
                                           * chunks of one pipelined host batch use one build) */
 
+std::atomic<long long> g_inflight_hint{0}; /* dart_se3mpc_set_inflight_hint: problems the caller keeps in flight */
+
 KernelChoice *pick_kernel(int N, long long B, bool rows = false)
 {
     if (g_batch_hint > B) B = g_batch_hint;
+    const long long inflight = g_inflight_hint.load(std::memory_order_relaxed);
+    if (inflight > B) B = inflight;
     if (rows) B = 1; /* row output exists in the latency builds only */
     int idx = N <= 4 ? 0 : N <= 8 ? 1 : N <= 16 ? 2 : N <= 32 ? 3 : 4;
     /* N <= 8: the 168-register build (3 resident blocks per SM) trades a few spills for 50 % more
@@ -178,6 +182,13 @@ extern "C" {
 int dart_abi_version(void) { return DART_SE3MPC_ABI_VERSION; }
 const char *dart_last_cuda_error(void) { return g_err; }
 int64_t dart_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int dart_se3mpc_set_inflight_hint(int64_t problems_in_flight)
+{
+    if (problems_in_flight < 0) return DART_E_BADARG;
+    g_inflight_hint.store(problems_in_flight, std::memory_order_relaxed);
+    return DART_OK;
+}
 void dart_count_launch_(void) { g_launches.fetch_add(1); }
 
 void dart_se3mpc_default_params(dart_se3mpc_params *p)

@@ -554,6 +554,30 @@ def extract_batch(thrust_vectors, config: Optional[SE3MPCConfig] = None, *, mass
             h[:, 6 * N: 9 * N].reshape(B, N, 3), h[:, 9 * N:])
 
 
+class steps_in_flight:
+    """Context manager for a caller that keeps several batched solves in flight on different CUDA
+    streams (a planning server working through a stream of steps): tells the library how many
+    problems that is in total, so the build is chosen for the machine's real load instead of one
+    launch's B (`dart_se3mpc_set_inflight_hint`).  Four 4 096-problem steps in flight run at
+    14.4 us per step on a B200; one at a time takes 24.7 us.
+
+    >>> with dp.planner.steps_in_flight(4 * B):
+    ...     for k, ws in enumerate(workspaces):           # resident inputs, one workspace per step
+    ...         ws.solve_device(streams[k % 4])
+    """
+
+    def __init__(self, problems: int):
+        self.problems = int(problems)
+
+    def __enter__(self):
+        _cabi.check(_cabi.lib().dart_se3mpc_set_inflight_hint(self.problems), "dart_se3mpc_set_inflight_hint")
+        return self
+
+    def __exit__(self, *exc):
+        _cabi.lib().dart_se3mpc_set_inflight_hint(0)
+        return False
+
+
 def plan_batch(positions, velocities, goals, config: Optional[SE3MPCConfig] = None, *,
                mass: float = 1.5, gravity: float = 9.81, dt: Optional[float] = None,
                has_goal=None, x_warm=None, warm_mask=None, gradient_mode: int = 0,

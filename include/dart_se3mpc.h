@@ -219,6 +219,16 @@ void dart_se3mpc_release_thread_workspace(void);
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t dart_launch_count(void);
 
+/* A caller that keeps several launches in flight on different streams (a stream of planning
+ * steps, each a batch of its own) says how many problems that is in total: the build is then
+ * chosen for that number instead of one launch's B -- four 4 096-problem steps in flight fill the
+ * machine like one 16 384-problem launch, and the register-capped throughput build (3 resident
+ * blocks per SM) serves them at 14.4 us per step where one step at a time takes 24.7 us in the
+ * latency build.  0 restores the per-launch choice.  Process-wide; row-output launches always use
+ * the latency build.  (No counterpart in the reference: its planner solves one problem per call,
+ * se3_mpc_planner.py:215-228.) */
+int dart_se3mpc_set_inflight_hint(int64_t problems_in_flight);
+
 /* Name, registers and launch geometry of the solve kernel chosen for (horizon, B). */
 int dart_se3mpc_kernel_info(const dart_se3mpc_params *params, int64_t B, int32_t *lanes,
                             int32_t *block_threads, int32_t *grid_blocks, int32_t *smem_bytes,

@@ -395,6 +395,47 @@ def test_gpu_build_variants_agree(oracle_mod, monkeypatch):
         np.testing.assert_allclose(got.body_rates, base.body_rates, rtol=0, atol=1e-9)
 
 
+def test_steps_in_flight_on_several_streams(oracle_mod):
+    """A stream of planning steps with four in flight (one CUDA stream each) under
+    `steps_in_flight`: the library picks the throughput build for the total load; every step's
+    result equals the step solved alone (counters identical, x to contraction rounding) and the
+    oracle's; the hint is process-wide and is reset on exit."""
+    import ctypes as C
+    import torch
+    import dart_planner_b200 as dp
+    from dart_planner_b200 import _cabi
+    from dart_planner_b200.config import make_params
+    from dart_planner_b200.planner import BatchWorkspace, steps_in_flight
+    B, D, K = 4096, 4, 12
+    params = make_params(dp.SE3MPCConfig(prediction_horizon=8, dt=0.1))
+    L = _cabi.lib()
+    info = [C.c_int32() for _ in range(5)]
+    L.dart_se3mpc_kernel_info(C.byref(params), B, *[C.byref(i) for i in info])
+    regs_alone = info[4].value
+    steps = [bench_inputs(300 + k, B, 1.0) for k in range(K)]
+    alone = [dp.plan_batch(*st, dp.SE3MPCConfig(prediction_horizon=8, dt=0.1), to_host=True) for st in steps]
+    ws = [BatchWorkspace(params, B, pinned=False, outputs="all") for _ in range(K)]
+    for w, st in zip(ws, steps):
+        w.set_inputs_device(*st)
+    streams = [torch.cuda.Stream() for _ in range(D)]
+    torch.cuda.synchronize()
+    with steps_in_flight(D * B):
+        L.dart_se3mpc_kernel_info(C.byref(params), B, *[C.byref(i) for i in info])
+        assert info[4].value <= 168 < regs_alone          # the register-capped throughput build
+        sols = [w.solve_device(streams[k % D]) for k, w in enumerate(ws)]
+        torch.cuda.synchronize()
+    L.dart_se3mpc_kernel_info(C.byref(params), B, *[C.byref(i) for i in info])
+    assert info[4].value == regs_alone
+    for k in (0, 5, 11):
+        got = sols[k].numpy()
+        np.testing.assert_array_equal(got.nfev, alone[k].nfev)
+        np.testing.assert_array_equal(got.status, alone[k].status)
+        np.testing.assert_allclose(got.x, alone[k].x, rtol=0, atol=1e-11)
+    ref = oracle_mod.solve_batch(oracle_mod.make_params(horizon=8, dt=0.1), *steps[7], nthreads=16)
+    _compare(sols[7].numpy(), ref)
+    assert L.dart_se3mpc_set_inflight_hint(-1) != 0
+
+
 def _compare_solutions(sol, ref, what):
     """Solution-level parity for configurations away from the reference's defaults.  With other
     weights / tighter tolerances many solves end in the degenerate line-search regime (status 2,

@@ -469,46 +469,81 @@ def main():
     else:
         e2e_call = lambda: ws.solve_staged(stream)
     ms_e2e = time_steps(torch, e2e_call, flush, min(args.steps, 50), args.warmup, stream)   # one step at a time
-    # The headline: the same call as a stream of steps, E2E_DEPTH of them in flight (one workspace
-    # + stream each, `solve_rows(wait=False)`): the row write-back of one step (2.6 MB over PCIe)
+    # The headline: the same call as a stream of steps with several in flight (one workspace +
+    # stream each, `solve_rows(wait=False)`): the row write-back of one step (2.6 MB over PCIe)
     # overlaps the solve of the next.  Every step reads its inputs from pinned host memory and
     # leaves its result rows in pinned host memory inside the timed region (start event before the
-    # first launch, end event after the last stream has drained).
+    # first launch, end event after the last stream has drained).  How many steps in flight pay
+    # depends on the host: one GPU's link is busiest with three; eight GPUs writing into one host
+    # memory system saturate it with fewer (more in flight only adds contention).  All depths up to
+    # E2E_DEPTH are timed (K steps each, max over ranks) and the best is the headline; every
+    # depth's figure is in `e2e.by_depth`.
     slots = [ws_e2e]
     streams = [stream]
+    e2e_by_depth = {}
     if use_rows:
         for _ in range(E2E_DEPTH - 1):
             w = BatchWorkspace(params, B, pinned=True, outputs="solution")
             w.stage_host_inputs(p0, v0, goal)
             slots.append(w)
             streams.append(torch.cuda.Stream())
-        for i in range(max(args.warmup, 2 * len(slots))):
-            slots[i % len(slots)].solve_rows(streams[i % len(slots)], wait=False)
-        torch.cuda.synchronize()
-        for w in slots:
-            w.h_rows.zero_()
-        barrier()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda._sleep(2_000_000)
-        s0.record(stream)
-        for st in streams[1:]:
-            st.wait_event(s0)
-        for i in range(args.steps):
-            slots[i % len(slots)].solve_rows(streams[i % len(slots)], wait=False)
-        for st in streams[1:]:
-            ev = torch.cuda.Event()
-            ev.record(st)
-            stream.wait_event(ev)
-        s1.record(stream)
-        torch.cuda.synchronize()
-        e2e_stream_ms = float(s0.elapsed_time(s1))
+
+        def e2e_stream(depth):
+            for i in range(max(args.warmup, 2 * depth)):
+                slots[i % depth].solve_rows(streams[i % depth], wait=False)
+            torch.cuda.synchronize()
+            for w in slots[:depth]:
+                w.h_rows.zero_()
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda._sleep(2_000_000)
+            s0.record(stream)
+            for st in streams[1:depth]:
+                st.wait_event(s0)
+            for i in range(args.steps):
+                slots[i % depth].solve_rows(streams[i % depth], wait=False)
+            for st in streams[1:depth]:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                stream.wait_event(ev)
+            s1.record(stream)
+            torch.cuda.synchronize()
+            tt = torch.tensor([float(s0.elapsed_time(s1))], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+
+        for depth in range(E2E_DEPTH, 0, -1):
+            e2e_by_depth[depth] = e2e_stream(depth)
+        e2e_depth = min(e2e_by_depth, key=e2e_by_depth.get)
+        e2e_stream_ms = e2e_by_depth[e2e_depth]
+        if e2e_depth != 1:
+            e2e_stream(e2e_depth)      # leave every used slot holding a result of the chosen configuration
     else:
+        e2e_depth = 1
         e2e_stream_ms = float(sum(ms_e2e)) * args.steps / len(ms_e2e)
+    # what the host side can take: all ranks copy 64 MiB blocks device -> pinned host at once
+    # (copy engine, 8 copies each), the ceiling for any result path into host memory on this box
+    probe_d = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+    probe_h = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
+    probe_h.copy_(probe_d)
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record(stream)
+    for _ in range(8):
+        probe_h.copy_(probe_d, non_blocking=True)
+    c1.record(stream)
+    torch.cuda.synchronize()
+    tt = torch.tensor([float(c0.elapsed_time(c1))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    d2h_gbs_aggregate = world * 8 * (64 << 20) / (float(tt.item()) * 1e-3) / 1e9
+    del probe_d, probe_h
     dev = ws.solve_device(stream).numpy()
     if use_rows:    # what arrived in host memory is the resident solve's result, bit for bit
         got = HostSolution.from_solution_rows(N, ws_e2e.h_rows.numpy()[:B], params)
         e2e_checked = True
-        for w in slots:     # every slot's host block holds the resident solve's result
+        for w in slots[:e2e_depth]:     # every slot's host block holds the resident solve's result
             got = HostSolution.from_solution_rows(N, w.h_rows.numpy()[:B], params)
             e2e_checked = e2e_checked and bool(
                 np.array_equal(got.x, dev.x) and np.array_equal(got.cost, dev.cost)
@@ -520,11 +555,16 @@ def main():
         e2e_checked = bool(np.array_equal(ws.h_out.numpy()[: 9 * N, :B].T, dev.x))
     sampler.active.clear()
     barrier()
-    t = torch.tensor([e2e_stream_ms, float(sum(ms_e2e))], dtype=torch.float64, device="cuda")
+    t = torch.tensor([float(sum(ms_e2e))], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * args.steps / (float(t[0].item()) * 1e-3)
-    e2e_single_value = world * B * len(ms_e2e) / (float(t[1].item()) * 1e-3)
+    e2e_value = world * B * args.steps / (e2e_stream_ms * 1e-3)        # already the max over ranks
+    e2e_single_value = world * B * len(ms_e2e) / (float(t[0].item()) * 1e-3)
+    e2e_ms_per_step = e2e_stream_ms / args.steps
+    if e2e_single_value > e2e_value:
+        # launch -> wait -> next (the host in the loop) beats every streamed depth: the ranks' writes
+        # into host memory collide less.  Seen on 8 GPUs; it is the same public call.
+        e2e_value, e2e_depth, e2e_ms_per_step = e2e_single_value, 0, float(t[0].item()) / len(ms_e2e)
     del slots[1:]
 
     # ---- BASELINE configs[3] / configs[4] on all GPUs of this launch ----------------------------
@@ -590,9 +630,14 @@ def main():
         "config": workload_config(args),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": ws.h2d_bytes,
                 "d2h_bytes_per_step": ws_e2e.d2h_bytes_rows if use_rows else ws.d2h_bytes,
-                "ms_per_step": e2e_stream_ms / args.steps, "steps_in_flight": E2E_DEPTH if use_rows else 1,
+                "ms_per_step": e2e_ms_per_step, "steps_in_flight": e2e_depth,
+                "by_depth": dict({"0 (launch, wait, next)": e2e_single_value},
+                                 **{str(k): world * B * args.steps / (v * 1e-3) for k, v in sorted(e2e_by_depth.items())}),
+                "host_d2h_ceiling": {"aggregate_gbs": d2h_gbs_aggregate, "per_gpu_gbs": d2h_gbs_aggregate / world,
+                                     "as_solves_per_s": d2h_gbs_aggregate * 1e9 / (ws_e2e.d2h_bytes_rows / B) if use_rows else None,
+                                     "note": "all ranks copying 64 MiB blocks device -> pinned host at once (copy engines)"},
                 "api": ("dart_planner_b200.planner.BatchWorkspace(outputs='solution').solve_rows(wait=False) "
-                        f"on {E2E_DEPTH} workspaces / streams in rotation (pinned host buffers; the kernel reads "
+                        f"on {max(e2e_depth, 1)} workspaces / streams in rotation (pinned host buffers; the kernel reads "
                         "them and writes one row [x | cost | counters] per problem over PCIe itself, no separate "
                         "copies; derived arrays evaluated lazily on the host)")
                 if use_rows else "dart_planner_b200.planner.BatchWorkspace.solve_staged (pinned host buffers)",

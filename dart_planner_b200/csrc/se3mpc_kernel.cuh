@@ -55,7 +55,37 @@ struct SolveArgs {
     unsigned long long *queue;
     /* two-phase schedule: context slots, grid x (2 GPB - 1) x ctx_doubles(1) doubles */
     double *stash;
+    /* Long solves first (throughput builds, cold starts, large batches; off when prio_count ==
+     * nullptr).  A problem that starts within ~1 m of its goal ends in the reference's degenerate
+     * line-search regime -- two searches of 20 evaluations, ~4x the serial work of a normal solve
+     * -- and a launch lasts until the last of them is done, so one that is handed out late extends
+     * the launch by its own length (65 536 problems: 238 vs 304 us, profiles/README.md).  A scan
+     * kernel in front of the solve lists the problems with |goal - p0|^2 < prio_r2 (at most
+     * PRIO_CAP of them; a longer list, or one longer than B/64, switches the feature off for the
+     * launch).  The solve does not wait for the scan: it is launched as a programmatic dependent of
+     * it, every block's first round is a regular one, and only a block that comes back for more
+     * waits for the scan's completion (long past by then) and reads the list.  Tickets: G = grid
+     * size; t < G: regular round t; G <= t < G + P: priority round (members below G*GPB were
+     * solved in the first rounds already); later t: regular round t - P, members of the list
+     * skipped.  Scheduling only: which sub-warp solves a problem when has no effect on its result.
+     * prio_count is reset by the last block of the solve (the slot is reused by a later launch). */
+    int *prio_list;
+    unsigned *prio_count;
+    double prio_r2;
 };
+constexpr int PRIO_CAP = 16384;
+
+/* member of the priority list?  (the same predicate in the scan kernel and in the solve kernel) */
+__device__ __forceinline__ bool starts_near_goal(const SolveArgs &A, long long b)
+{
+    if (A.has_goal && A.has_goal[b] == 0) return false;
+    const double dx = __ldg(A.goal + b) - __ldg(A.p0 + b);
+    const double dy = __ldg(A.goal + A.ld + b) - __ldg(A.p0 + A.ld + b);
+    const double dz = __ldg(A.goal + 2 * A.ld + b) - __ldg(A.p0 + 2 * A.ld + b);
+    return dx * dx + dy * dy + dz * dz < A.prio_r2;
+}
+
+__global__ void __launch_bounds__(256) se3mpc_prio_scan_kernel(const __grid_constant__ SolveArgs A);
 
 /* doubles of one result row (before padding) and the padded stride; 0 when the row does not fit
  * the per-problem shared block it is staged in */
@@ -114,9 +144,12 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
      * problem's start and FIRST iteration (finished: results out; else its context goes to the
      * block's stash), 2 = a stashed problem (`alive` = this sub-warp has one, taken from slot
      * `b_in`) continues to the end, the block in lock step. */
-    auto solve_one = [&](const long long b_in, const bool alive, const int phase) {
-        (void)alive;
-        bool refused = false;
+    auto solve_one = [&](const long long b_in, const bool alive, const int phase, const bool skip_near = false) {
+        /* a padding sub-warp (lock-step builds: ragged last round, a skipped member of the priority
+         * list) keeps the block's barriers company but starts no solve.  (Starting one and cutting
+         * it after the first evaluation, so that `refused` stays a compile-time false in the
+         * cold-start kernels, was measured: 1 % slower.) */
+        bool refused = !alive;
         long long b = b_in;
         SolverT sv(P, sm, ws, wy);
         if (GM == 2) {
@@ -138,6 +171,12 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
             if (phase != 2) sv.goal[c] = __ldg(A.goal + c * A.ld + b);
         }
         if (phase != 2) sv.has_goal = A.has_goal ? (A.has_goal[b] != 0) : true;
+        if (skip_near) {
+            /* a member of the priority list met in a regular round: solved (or about to be) in a
+             * priority round.  The predicate of starts_near_goal on the values just loaded. */
+            const double dx = sv.goal[0] - p0[0], dy = sv.goal[1] - p0[1], dz = sv.goal[2] - p0[2];
+            if (sv.has_goal && dx * dx + dy * dy + dz * dz < A.prio_r2) refused = true;
+        }
         const bool warm = phase != 2 && A.x_warm != nullptr && (A.warm_mask == nullptr || A.warm_mask[b] != 0);
         if (phase == 2) {
             /* nothing to start */
@@ -151,7 +190,7 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
 #pragma unroll
                 for (int tt = 0; tt < TPL; ++tt)
                     tilted |= (sv.x[tt * 9 + 6] != 0.0 || sv.x[tt * 9 + 7] != 0.0) ? 1 : 0;
-                if (sv.grp.ori(tilted)) { /* broken promise: no solve, say so */
+                if (sv.grp.ori(tilted) && alive) { /* broken promise: no solve, say so */
                     if ((MINB < 3) && A.rows) {
                         double *row = A.rows + b * A.row_stride;
                         const int nx = (A.rows_kind == 1 ? 3 : 9) * N, nd = (A.rows_kind == 1 ? 3 : (A.rows_kind == 2 ? 9 : 19)) * N;
@@ -365,14 +404,40 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
     } else if constexpr (SCHED == 2) {
         __shared__ long long s_ticket;
         const long long rounds = (A.B + GPB - 1) / GPB;
+        const long long G = gridDim.x;
+        bool known = (A.prio_count == nullptr) || rounds <= G; /* no list, or every round is a first round */
+        long long npri = 0, pr_rounds = 0;
         for (;;) {
             __syncthreads();
             if (threadIdx.x == 0) s_ticket = (long long)atomicAdd(A.queue, 1ull);
             __syncthreads();
             const long long blk = s_ticket;
-            if (blk >= rounds) break;
-            const long long b = blk * GPB + gib;
-            solve_one(b < A.B ? b : A.B - 1, b < A.B, 0);
+            if (blk >= G && !known) {
+                /* the scan kernel this launch depends on has completed: read its list.  Used when it
+                 * holds a small part of the batch (a population that sits at its goals is not a set
+                 * of stragglers) and fits */
+#if defined(__CUDA_ARCH__)
+                asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+                const long long n = (long long)__ldcg(A.prio_count);
+                npri = (n > 0 && n <= PRIO_CAP && n * 64 <= A.B) ? n : 0;
+                pr_rounds = (npri + GPB - 1) / GPB;
+                known = true;
+            }
+            if (blk >= rounds + pr_rounds) break;
+            /* ONE call site: the solve is inlined once */
+            long long b;
+            bool alive;
+            if (blk >= G && blk < G + pr_rounds) {
+                const long long i = (blk - G) * GPB + gib;
+                b = (i < npri) ? (long long)__ldcg(A.prio_list + i) : 0;
+                alive = i < npri && b >= G * GPB;
+            } else {
+                const long long br = (blk < G ? blk : blk - pr_rounds) * GPB + gib;
+                b = br < A.B ? br : A.B - 1;
+                alive = br < A.B;
+            }
+            solve_one(b, alive, 0, blk >= G + pr_rounds && npri > 0);
         }
     } else if constexpr (SCHED == 4) {
         /* Two-phase schedule.  The solves differ 3x in length (1 to 3 iterations on the bench
@@ -430,6 +495,7 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
             if (atomicAdd(A.queue + 1, 1ull) == (unsigned long long)gridDim.x - 1ull) {
                 A.queue[0] = 0ull;
                 A.queue[1] = 0ull;
+                if (A.prio_count) *A.prio_count = 0u;
                 __threadfence();
             }
         }

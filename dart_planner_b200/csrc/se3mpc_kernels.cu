@@ -17,6 +17,19 @@
 
 using namespace dartb200;
 
+namespace dartb200 {
+__global__ void __launch_bounds__(256) se3mpc_prio_scan_kernel(const __grid_constant__ SolveArgs A)
+{
+    /* the solve behind this kernel may start right away: its first rounds do not need the list */
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < A.B; b += (long long)gridDim.x * blockDim.x)
+        if (starts_near_goal(A, b)) {
+            const unsigned slot = atomicAdd(A.prio_count, 1u);
+            if (slot < (unsigned)PRIO_CAP) A.prio_list[slot] = (int)b;
+        }
+}
+} /* namespace dartb200 */
+
 namespace {
 
 std::atomic<long long> g_launches{0};
@@ -70,6 +83,12 @@ struct StashBuf {
 };
 StashBuf g_stash[64][STASH_RING];
 unsigned g_stash_next[64] = {0};
+/* priority lists of the throughput builds ("long solves first", se3mpc_kernel.cuh): the same
+ * kind of ring, one list per launch in flight: [count (16 bytes) | B problem indices] */
+constexpr int PRIO_RING = 8;
+constexpr long long PRIO_MIN_B = 16384; /* below this a launch is a wave or two: nothing to reorder */
+StashBuf g_prio[64][PRIO_RING];
+unsigned g_prio_next[64] = {0};
 
 size_t stash_bytes_for(const KernelChoice &k, long long grid)
 {
@@ -247,7 +266,7 @@ static int launch_solve(const dart_se3mpc_params *params, const SolveArgs &a, vo
     SolveArgs args_copy = a;
     void *args[] = {(void *)&P, (void *)&args_copy};
     const long long grid_blocks = grid_for(*k, a.B);
-    cudaEvent_t stash_event = nullptr;
+    cudaEvent_t stash_event = nullptr, prio_event = nullptr;
     {
         /* ticket counters of the dynamic schedules: a ring of self-re-arming pairs per device, one
          * pair per launch in flight (a pair is reused 256 launches later) */
@@ -260,7 +279,49 @@ static int launch_solve(const dart_se3mpc_params *params, const SolveArgs &a, vo
             if (qe != cudaSuccess) return set_err(qe, "cudaMalloc(ticket counters)");
         }
         args_copy.queue = g_queue[dev] + 2 * (g_queue_next[dev]++ % QUEUE_SLOTS);
-        if (k->minb >= 3) {
+        /* long solves first: cold starts of a large batch in a throughput build (the predicate
+         * is about cold starts; a warm-started population near its goals is not a set of stragglers).
+         * Near-goal radius: where the position term of the start's objective, ~ w_pos N r^2 / 3,
+         * falls below the scale of the thrust term the reference's gradient mis-states,
+         * ~ w_thrust (m g)^2 N / 3 -- a scheduling heuristic, results do not depend on it. */
+        if (k->minb >= 3 && DART_THROUGHPUT_SCHED == 2 && a.B >= PRIO_MIN_B && a.B < (1ll << 31) &&
+            a.x_warm == nullptr && params->w_pos > 0.0 && !getenv("DART_SE3MPC_NO_PRIO")) {
+            StashBuf &pb = g_prio[dev][g_prio_next[dev]++ % PRIO_RING];
+            const size_t need = 16 + (size_t)PRIO_CAP * sizeof(int); /* fixed: allocated once per slot */
+            if (pb.done) {
+                cudaError_t se = cudaStreamWaitEvent((cudaStream_t)cuda_stream, pb.done, 0);
+                if (se != cudaSuccess) return set_err(se, "cudaStreamWaitEvent(priority list)");
+            } else {
+                cudaError_t se = cudaEventCreateWithFlags(&pb.done, cudaEventDisableTiming);
+                if (se != cudaSuccess) return set_err(se, "cudaEventCreate(priority list)");
+            }
+            if (pb.bytes < need) {
+                if (pb.ptr) {
+                    cudaEventSynchronize(pb.done);
+                    cudaFree(pb.ptr);
+                }
+                pb.ptr = nullptr;
+                pb.bytes = 0;
+                cudaError_t se = cudaMalloc(&pb.ptr, need);
+                if (se == cudaSuccess) se = cudaMemsetAsync(pb.ptr, 0, 16, (cudaStream_t)cuda_stream);
+                if (se != cudaSuccess) return set_err(se, "cudaMalloc(priority list)");
+                pb.bytes = need;
+            }
+            args_copy.prio_count = reinterpret_cast<unsigned *>(pb.ptr);
+            args_copy.prio_list = reinterpret_cast<int *>(reinterpret_cast<char *>(pb.ptr) + 16);
+            const double hover = params->mass * params->gravity;
+            args_copy.prio_r2 = params->w_thrust * hover * hover / params->w_pos * (double)params->horizon;
+            prio_event = pb.done;
+            long long sblocks = (a.B + 255) / 256;
+            const long long cap = 8ll * (g_sms > 0 ? g_sms : 148);
+            if (sblocks > cap) sblocks = cap;
+            void *sargs[] = {(void *)&args_copy};
+            cudaError_t se = cudaLaunchKernel((const void *)se3mpc_prio_scan_kernel, dim3((unsigned)sblocks), dim3(256),
+                                              sargs, 0, (cudaStream_t)cuda_stream);
+            if (se != cudaSuccess) return set_err(se, "cudaLaunchKernel(se3mpc_prio_scan)");
+            g_launches.fetch_add(1);
+        }
+        if (k->minb >= 3 && DART_THROUGHPUT_SCHED == 4) {
             StashBuf &sb = g_stash[dev][g_stash_next[dev]++ % STASH_RING];
             const size_t need = stash_bytes_for(*k, grid_blocks);
             if (sb.done) {
@@ -287,10 +348,27 @@ static int launch_solve(const dart_se3mpc_params *params, const SolveArgs &a, vo
     }
     const int cold = ((a.x_warm == nullptr || a.no_tilt_promise) && !getenv("DART_SE3MPC_NO_COLD")) ? 0 : 1;
     const void *fn = k->set.fn[params->gradient_mode][cold];
-    cudaError_t e = cudaLaunchKernel(fn, dim3((unsigned)grid_blocks), dim3(k->block), args,
-                                     smem_bytes(*k), (cudaStream_t)cuda_stream);
+    cudaError_t e;
+    if (prio_event) {
+        /* programmatic dependent launch: the solve may begin while the scan in front of it runs */
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)grid_blocks);
+        cfg.blockDim = dim3(k->block);
+        cfg.dynamicSmemBytes = smem_bytes(*k);
+        cfg.stream = (cudaStream_t)cuda_stream;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelExC(&cfg, fn, args);
+    } else
+        e = cudaLaunchKernel(fn, dim3((unsigned)grid_blocks), dim3(k->block), args, smem_bytes(*k),
+                             (cudaStream_t)cuda_stream);
     if (e != cudaSuccess) return set_err(e, "cudaLaunchKernel(se3mpc_solve)");
     if (stash_event) cudaEventRecord(stash_event, (cudaStream_t)cuda_stream);
+    if (prio_event) cudaEventRecord(prio_event, (cudaStream_t)cuda_stream);
     g_launches.fetch_add(1);
     return DART_OK;
 }

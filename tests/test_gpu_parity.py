@@ -436,6 +436,41 @@ def test_steps_in_flight_on_several_streams(oracle_mod):
     assert L.dart_se3mpc_set_inflight_hint(-1) != 0
 
 
+@pytest.mark.parametrize("near_fraction", [0.0005, 0.3, 0.6])    # used / ignored (too many) / ignored (list overflows)
+def test_long_solves_first_schedule_changes_no_result(oracle_mod, monkeypatch, near_fraction):
+    """Large cold batches in the throughput build are scheduled "long solves first": a scan kernel
+    lists the problems that start within ~1 m of their goal (they end in the degenerate
+    line-search regime, ~4x the work) and the first tickets after every block's first round serve
+    that list.  Scheduling only: with the list (a few members: used; 30 % of the batch: ignored),
+    without it (DART_SE3MPC_NO_PRIO), ragged batch, has_goal mask -- identical results, and the
+    oracle's."""
+    import dart_planner_b200 as dp
+    rng = np.random.default_rng(808)
+    B = 40000 + 7
+    p0, v0, goal = bench_inputs(809, B, 0.0)
+    near = rng.random(B) < near_fraction
+    near[-300:] |= rng.random(300) < 0.05                 # some in the last rounds of the batch
+    near[:9000:1500] = True                               # some inside the first rounds (solved there, not twice)
+    goal[near] = p0[near] + rng.normal(0, 0.25, (int(near.sum()), 3))
+    hg = (np.arange(B) % 11 != 0).astype(np.uint8)
+    cfg = dp.SE3MPCConfig(prediction_horizon=8, dt=0.1)
+    monkeypatch.delenv("DART_SE3MPC_NO_PRIO", raising=False)
+    with_list = dp.plan_batch(p0, v0, goal, cfg, has_goal=hg, to_host=True)
+    monkeypatch.setenv("DART_SE3MPC_NO_PRIO", "1")
+    without = dp.plan_batch(p0, v0, goal, cfg, has_goal=hg, to_host=True)
+    monkeypatch.delenv("DART_SE3MPC_NO_PRIO")
+    for k in ("x", "cost", "nit", "nfev", "status", "attitudes", "body_rates", "thrusts"):
+        np.testing.assert_array_equal(getattr(with_list, k), getattr(without, k), err_msg=k)
+    assert (with_list.nfev[near & (hg != 0)] > 8).any()      # the planted problems are long solves
+    sub = np.r_[np.where(near)[0][:400], rng.integers(0, B, 2000)]
+    ref = oracle_mod.solve_batch(oracle_mod.make_params(horizon=8, dt=0.1), p0[sub], v0[sub], goal[sub],
+                                 has_goal=hg[sub], nthreads=16)
+    relf = np.abs(with_list.cost[sub] - ref.cost) / np.maximum(np.abs(ref.cost), 1.0)
+    same = (with_list.nit[sub] == ref.nit) & (with_list.nfev[sub] == ref.nfev) & (with_list.status[sub] == ref.status)
+    assert same.mean() >= 0.97 and (relf[same] <= COST_RTOL).all()
+    assert np.abs(with_list.x[sub] - ref.x)[same].max() <= CTRL_ATOL
+
+
 def _compare_solutions(sol, ref, what):
     """Solution-level parity for configurations away from the reference's defaults.  With other
     weights / tighter tolerances many solves end in the degenerate line-search regime (status 2,

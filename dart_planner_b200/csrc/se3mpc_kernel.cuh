@@ -404,34 +404,42 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
     } else if constexpr (SCHED == 2) {
         __shared__ long long s_ticket;
         const long long rounds = (A.B + GPB - 1) / GPB;
-        const long long G = gridDim.x;
-        bool known = (A.prio_count == nullptr) || rounds <= G; /* no list, or every round is a first round */
-        long long npri = 0, pr_rounds = 0;
+        /* the list's size lives in shared memory (block-uniform, read once per round): it would
+         * otherwise hold registers through the whole solve.  -1 = not read yet */
+        __shared__ int s_npri;
+        if (threadIdx.x == 0) s_npri = (A.prio_count == nullptr || rounds <= (long long)gridDim.x) ? 0 : -1;
         for (;;) {
             __syncthreads();
-            if (threadIdx.x == 0) s_ticket = (long long)atomicAdd(A.queue, 1ull);
+            if (threadIdx.x == 0) {
+                const long long tk = (long long)atomicAdd(A.queue, 1ull);
+                s_ticket = tk;
+                if (tk >= (long long)gridDim.x && s_npri < 0) {
+                    /* the scan kernel this launch depends on has completed: read its list.  Used
+                     * when it holds a small part of the batch (a population that sits at its goals
+                     * is not a set of stragglers) and fits */
+#if defined(__CUDA_ARCH__)
+                    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+                    const long long n = (long long)__ldcg(A.prio_count);
+                    s_npri = (n > 0 && n <= PRIO_CAP && n * 64 <= A.B) ? (int)n : 0;
+                }
+            }
             __syncthreads();
             const long long blk = s_ticket;
-            if (blk >= G && !known) {
-                /* the scan kernel this launch depends on has completed: read its list.  Used when it
-                 * holds a small part of the batch (a population that sits at its goals is not a set
-                 * of stragglers) and fits */
-#if defined(__CUDA_ARCH__)
-                asm volatile("griddepcontrol.wait;" ::: "memory");
-#endif
-                const long long n = (long long)__ldcg(A.prio_count);
-                npri = (n > 0 && n <= PRIO_CAP && n * 64 <= A.B) ? n : 0;
-                pr_rounds = (npri + GPB - 1) / GPB;
-                known = true;
-            }
+            const int G = (int)gridDim.x;
+            const int npri = blk >= G ? s_npri : 0;
+            const int pr_rounds = (npri + GPB - 1) / GPB;
             if (blk >= rounds + pr_rounds) break;
             /* ONE call site: the solve is inlined once */
             long long b;
             bool alive;
             if (blk >= G && blk < G + pr_rounds) {
-                const long long i = (blk - G) * GPB + gib;
+                const int i = (int)(blk - G) * GPB + gib;
+#if defined(__CUDA_ARCH__)
+                asm volatile("griddepcontrol.wait;" ::: "memory"); /* satisfied long ago: every reader of the list says so */
+#endif
                 b = (i < npri) ? (long long)__ldcg(A.prio_list + i) : 0;
-                alive = i < npri && b >= G * GPB;
+                alive = i < npri && b >= (long long)G * GPB;
             } else {
                 const long long br = (blk < G ? blk : blk - pr_rounds) * GPB + gib;
                 b = br < A.B ? br : A.B - 1;

@@ -233,8 +233,8 @@ def sharded_config_legs(torch, dist, dp, params, world, rank, stream, dt):
     v0 = rng.normal(0, 0.5, (Bg, 3))
     goal = np.tile([10.0, 0.0, 5.0], (Bg, 1))
     lo, hi = shard_range(Bg, world, rank)
-    for outputs in ("solution", "all"):
-        solver = ShardedSolver(params, outputs=outputs)
+    for outputs, transport in (("solution", "host_block"), ("solution", "gather"), ("all", "gather")):
+        solver = ShardedSolver(params, outputs=outputs, transport=transport)
         solver.stage(p0[lo:hi], v0[lo:hi], goal[lo:hi], presliced=True, global_B=Bg)
         for _ in range(2):
             solver.run()
@@ -250,10 +250,15 @@ def sharded_config_legs(torch, dist, dp, params, world, rank, stream, dt):
             times.append(max_over_ranks(a.elapsed_time(b)))
         ms = statistics.mean(times)
         leg = {"value": Bg / (ms * 1e-3), "unit": UNIT, "ms": ms, "n_gpus": world, "scaling": "strong",
-               "row_bytes": None, "gather": "one NCCL gather of packed rows to rank 0 + one pinned copy per slice"
-               if world > 1 else "single GPU: one pinned copy of the packed rows"}
+               "row_bytes": None}
+        if transport == "host_block":
+            leg["transport"] = ("no collective: every rank's kernel writes the rows of its slice straight into ONE "
+                                "page-locked host block shared by the ranks (its own PCIe link), a barrier ends the call")
+        else:
+            leg["transport"] = ("one NCCL gather of packed rows to rank 0 + one pinned copy per slice"
+                                if world > 1 else "single GPU: one pinned copy of the packed rows")
         if rank == 0:
-            leg["row_bytes"] = int(solver._pinned.shape[1] * 8)
+            leg["row_bytes"] = int((solver._block.stride if transport == "host_block" else solver._pinned.shape[1]) * 8)
             # bit-identity: rank 0 alone solves a sample spread over every shard
             idx = np.arange(0, Bg, 257)
             alone = dp.plan_batch(p0[idx], v0[idx], goal[idx], dp.SE3MPCConfig(prediction_horizon=int(params.horizon), dt=dt),
@@ -263,7 +268,11 @@ def sharded_config_legs(torch, dist, dp, params, world, rank, stream, dt):
                 and np.array_equal(sol.nfev[idx], alone.nfev) and np.array_equal(sol.status[idx], alone.status))
             leg["sample"] = int(len(idx))
             leg["nit_hist"] = np.bincount(sol.nit, minlength=4).tolist()
-        out[f"configs[3] 1 Mi Monte-Carlo solves sharded by problem index, {outputs} rows gathered to rank 0 host memory"] = leg
+        how = "written into a shared host block" if transport == "host_block" else "gathered to rank 0 host memory"
+        out[f"configs[3] 1 Mi Monte-Carlo solves sharded by problem index, {outputs} rows {how}"] = leg
+        if transport == "host_block":
+            sync_all()
+            solver._block.close()
         del solver, sol
     # ---- configs[4]: 65536 drones x 100 replans (10 s at 10 Hz), warm starts, resident state ----
     Bd = 65536

@@ -477,14 +477,17 @@ class BatchWorkspace:
             stream.synchronize()
         return self.h_rows[: self.B]
 
-    def solve_rows_device(self, stream=None):
-        """Row output into DEVICE memory from the resident inputs (what `ShardedSolver` gathers:
-        one contiguous row per problem, so a rank's slice is one contiguous block).  Returns the
-        (B, stride) device tensor; asynchronous."""
+    def solve_rows_device(self, stream=None, rows_ptr: Optional[int] = None):
+        """Row output from the resident inputs into DEVICE memory (what `ShardedSolver` gathers:
+        one contiguous row per problem, so a rank's slice is one contiguous block); returns the
+        (B, stride) device tensor.  With ``rows_ptr`` the rows go to that address instead -- B rows
+        of `row_stride` doubles, 128-byte aligned, device memory or page-locked mapped host memory
+        (the shared block of `ShardedSolver(transport="host_block")`) -- and nothing is returned.
+        Asynchronous."""
         torch = _torch()
         if self.row_stride <= 0:
             raise RuntimeError("row output needs a horizon of at most 25 steps (64 for controls rows)")
-        if getattr(self, "d_rows", None) is None:
+        if rows_ptr is None and getattr(self, "d_rows", None) is None:
             self.d_rows = torch.zeros((self.ld, self.row_stride), dtype=torch.float64, device=self.device)
         stream = stream or torch.cuda.current_stream(self.device)
         es = 8 * self.ld
@@ -494,12 +497,12 @@ class BatchWorkspace:
             rc = _cabi.lib().dart_se3mpc_solve_batch_rows(
                 C.byref(self.params), self.B, self.ld, di, di + 3 * es, di + 6 * es,
                 _ptr(self.has_goal), _ptr(self.x_warm), _ptr(self.warm_mask),
-                self.d_rows.data_ptr(), self.row_stride, self.row_kind,
+                rows_ptr if rows_ptr is not None else self.d_rows.data_ptr(), self.row_stride, self.row_kind,
                 C.byref(g) if g is not None else None, float(self.safety_margin),
                 float(self.collision_threshold), 1 if (g is not None and self.row_kind != 1) else 0,
                 stream.cuda_stream)
         _cabi.check(rc, "dart_se3mpc_solve_batch_rows")
-        return self.d_rows[: self.B]
+        return None if rows_ptr is not None else self.d_rows[: self.B]
 
     def _solve_staged_pipelined(self):
         """Large batches: the C host entry splits the batch into chunks on two streams so the

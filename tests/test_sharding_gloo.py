@@ -103,6 +103,18 @@ def _rows_worker(rank, world, port, B, q):
                                     np.asarray(sol.thrusts).copy(), np.asarray(sol.body_rates).copy())
             else:
                 assert sol is None
+            # the same through the shared host block (no gather: every rank writes its slice)
+            hb = ShardedSolver(params, rows_fn=_oracle_rows_fn, outputs=outputs, transport="host_block")
+            s2 = hb.solve(p0, v0, goal)
+            s3 = hb.solve(p0, v0, goal, copy=True)                 # reuses the shared block
+            if rank == 0:
+                key = "thrust_vectors" if outputs == "controls" else "x"
+                assert np.array_equal(getattr(s2, key), res[outputs][0]) and np.array_equal(s2.cost, res[outputs][1])
+                assert np.array_equal(getattr(s3, key), res[outputs][0]) and np.array_equal(s3.nfev, sol.nfev)
+            else:
+                assert s2 is None and s3 is None
+            dist.barrier()
+            hb._block.close()
         if rank == 0:
             q.put(res)
         dist.barrier()

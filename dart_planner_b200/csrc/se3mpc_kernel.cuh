@@ -190,7 +190,7 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
 #pragma unroll
                 for (int tt = 0; tt < TPL; ++tt)
                     tilted |= (sv.x[tt * 9 + 6] != 0.0 || sv.x[tt * 9 + 7] != 0.0) ? 1 : 0;
-                if (sv.grp.ori(tilted) && alive) { /* broken promise: no solve, say so */
+                if (sv.grp.any(tilted != 0) && alive) { /* broken promise: no solve, say so */
                     if ((MINB < 3) && A.rows) {
                         double *row = A.rows + b * A.row_stride;
                         const int nx = (A.rows_kind == 1 ? 3 : 9) * N, nd = (A.rows_kind == 1 ? 3 : (A.rows_kind == 2 ? 9 : 19)) * N;

@@ -146,6 +146,29 @@ def test_core_random_configurations(oracle_mod, policy):
             np.testing.assert_allclose(got.attitudes[same], ref.attitudes[same], atol=1e-6)
 
 
+def test_core_on_demand_breakpoints_and_step_bound(oracle_mod, policy):
+    """The Cauchy breakpoints and the line search's step bound are formed on demand
+    (se3mpc_core.cuh: cauchy_walk, dcsrch).  On the benchmark mix neither is ever needed; this
+    regime -- small position / velocity weights, a 1e-5 tolerance, 50 iterations -- needs all three
+    slow paths (instrumented emulation, 1 500 problems: 23 walks cross a breakpoint, 1 938 searches
+    start with a bound <= 1, 5 152 bounds are formed after a refused trial point), so the kernel
+    core must still agree with the oracle there."""
+    import emu
+    from dart_planner_b200.config import SE3MPCConfig, make_params
+    rng = np.random.default_rng(11)
+    B, N = 1500, 8
+    kw = dict(position_weight=3.0, velocity_weight=0.1, max_iterations=50, convergence_tolerance=1e-5)
+    p0 = rng.uniform(-10, 10, (B, 3))
+    v0 = rng.uniform(-2, 2, (B, 3))
+    goal = np.concatenate([rng.uniform(-15, 15, (B, 2)), rng.uniform(3, 8, (B, 1))], axis=1)
+    ref = oracle_mod.solve_batch(oracle_mod.make_params(horizon=N, dt=0.1, **kw), p0, v0, goal, nthreads=8)
+    got = emu.solve_batch(make_params(SE3MPCConfig(prediction_horizon=N, dt=0.1, **kw)), p0, v0, goal)
+    same = (got.nit == ref.nit) & (got.nfev == ref.nfev) & (got.status == ref.status)
+    assert same.mean() > 0.995, f"counter mismatches: {np.where(~same)[0][:10]}"
+    assert (np.abs(got.x - ref.x).max(axis=1)[same] < 1e-8).all()
+    assert ref.nit.max() > 5 and (ref.nfev - ref.nit).max() > 2   # long solves, refused trial points
+
+
 def test_core_chaotic_configuration_within_the_oracles_own_sensitivity(oracle_mod):
     """Where the reference algorithm is chaotic, the kernel core agrees with the oracle as well as
     the oracle agrees with ITSELF after moving every start position by one ulp."""

@@ -395,6 +395,27 @@ def test_gpu_build_variants_agree(oracle_mod, monkeypatch):
         np.testing.assert_allclose(got.body_rates, base.body_rates, rtol=0, atol=1e-9)
 
 
+@pytest.mark.parametrize("variant", [None, "5"], ids=["default-build", "throughput-build"])
+def test_gpu_on_demand_breakpoints_and_step_bound(oracle_mod, monkeypatch, variant):
+    """The regime in which the on-demand Cauchy breakpoints and the on-demand step bound of the
+    line search are all needed (tests/test_core_emulation.py has the counts): the CUDA path must
+    agree with the oracle there as it does where they are skipped."""
+    import dart_planner_b200 as dp
+    rng = np.random.default_rng(11)
+    B, N = 1500, 8
+    kw = dict(position_weight=3.0, velocity_weight=0.1, max_iterations=50, convergence_tolerance=1e-5)
+    p0 = rng.uniform(-10, 10, (B, 3))
+    v0 = rng.uniform(-2, 2, (B, 3))
+    goal = np.concatenate([rng.uniform(-15, 15, (B, 2)), rng.uniform(3, 8, (B, 1))], axis=1)
+    ref = oracle_mod.solve_batch(oracle_mod.make_params(horizon=N, dt=0.1, **kw), p0, v0, goal, nthreads=16)
+    if variant:
+        monkeypatch.setenv("DART_SE3MPC_VARIANT", variant)
+    sol = dp.plan_batch(p0, v0, goal, dp.SE3MPCConfig(prediction_horizon=N, dt=0.1, **kw), to_host=True)
+    same = (sol.nit == ref.nit) & (sol.nfev == ref.nfev) & (sol.status == ref.status)
+    assert same.mean() > 0.995, f"counter mismatches: {np.where(~same)[0][:10]}"
+    assert (np.abs(sol.x - ref.x).max(axis=1)[same] < 1e-8).all()
+
+
 def test_steps_in_flight_on_several_streams(oracle_mod):
     """A stream of planning steps with four in flight (one CUDA stream each) under
     `steps_in_flight`: the library picks the throughput build for the total load; every step's

@@ -20,6 +20,7 @@ UNITS = {
     "se3mpc_inst_l4.cu": [], "se3mpc_inst_l8.cu": [], "se3mpc_inst_l16.cu": [],
     "se3mpc_inst_l32.cu": [], "se3mpc_inst_l32x2.cu": [], "se3mpc_inst_l8_occ3.cu": [],
     "se3mpc_inst_l8_b64.cu": [], "se3mpc_inst_l16_occ3.cu": [], "se3mpc_inst_l32_occ3.cu": [],
+    "se3mpc_inst_l6.cu": [], "se3mpc_inst_l6_occ5.cu": [],
     "mapper_kernels.cu": ["-fmad=false"],
     "probe_kernels.cu": [],
 }
@@ -80,7 +81,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 # instantiations compiled with -DDART_NO_CLOSED_FORM (the published breakpoint walk also when no
 # pair is stored), everything else shared with the product build.  Never loaded by the product.
 NOCF_LIB = os.path.join(LIBDIR, "libdart_se3mpc_nocf.so")
-NOCF_UNITS = ["se3mpc_inst_l8.cu", "se3mpc_inst_l8_occ3.cu", "se3mpc_inst_l4.cu"]
+NOCF_UNITS = ["se3mpc_inst_l8.cu", "se3mpc_inst_l8_occ3.cu", "se3mpc_inst_l4.cu", "se3mpc_inst_l6.cu",
+              "se3mpc_inst_l6_occ5.cu"]
 
 
 def build_nocf() -> str:

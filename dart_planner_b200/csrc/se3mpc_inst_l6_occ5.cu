@@ -1,0 +1,6 @@
+/* instantiation unit: solve kernels <LANES, TPL, MINB, BLOCK> = <6, 1, 5, 64> (see se3mpc_kernel.cuh) */
+#include "se3mpc_kernel.cuh"
+
+namespace dartb200 {
+KernelSet kernel_set_l6_occ5() { return make_kernel_set<6, 1, 5, 64>(); }
+}

@@ -99,13 +99,30 @@ __host__ __device__ inline int row_stride_doubles(int N, int kind)
     return st <= SM_DOUBLES ? st : 0;
 }
 
+/* Problems (lane groups) per block and this thread's group.  LANES = 6: five groups per warp, the
+ * warp's last two lanes own no problem (`idle`; they follow the block's barriers and the warp's
+ * round loop, alias the warp's last group index and never start a solve). */
+template <int LANES, int BLOCK>
+struct GroupMap {
+    static constexpr int GPW = 32 / LANES;
+    static constexpr int GPB = (BLOCK / 32) * GPW;
+    __device__ static __forceinline__ bool idle() { return (LANES * GPW != 32) && (int)(threadIdx.x & 31) >= LANES * GPW; }
+    __device__ static __forceinline__ int gib()
+    {
+        const int g = (int)(threadIdx.x & 31) / LANES;
+        return (int)(threadIdx.x >> 5) * GPW + (g < GPW ? g : GPW - 1);
+    }
+};
+
 template <int LANES, int TPL, int BLOCK, int MINB, int GM, bool TILT>
 __global__ void __launch_bounds__(BLOCK, MINB)
 se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_constant__ SolveArgs A)
 {
     extern __shared__ double smem_all[];
-    constexpr int GPB = BLOCK / LANES; /* problems (groups) per block */
-    const int gib = threadIdx.x / LANES;
+    using GMap = GroupMap<LANES, BLOCK>;
+    constexpr int GPB = GMap::GPB; /* problems (groups) per block */
+    const int gib = GMap::gib();
+    const bool idle_lane = GMap::idle();
     double *sm = smem_all + gib * SM_DOUBLES;
     const int N = P.horizon;
     double ws[MMAX][9 * TPL], wy[MMAX][9 * TPL]; /* per-lane S / Y pairs (local memory, L1) */
@@ -129,7 +146,7 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
 #endif
     constexpr int SCHED = (MINB >= 3) ? DART_THROUGHPUT_SCHED : DART_LATENCY_SCHED;
     constexpr bool LOCK = (SCHED == 2) || (SCHED == 3);
-    using SolverT = Solver<SubWarp<LANES>, TPL, GM, (MINB >= 3), TILT>;
+    using SolverT = Solver<typename GroupOf<LANES>::type, TPL, GM, (MINB >= 3), TILT>;
     /* two-phase schedule (SCHED 4): contexts of the problems between their first iteration and
      * the rest of their solve, GPB - 1 left over + GPB new ones at most, per block, in global
      * memory (L2-resident: written once, read once) */
@@ -149,7 +166,7 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
          * list) keeps the block's barriers company but starts no solve.  (Starting one and cutting
          * it after the first evaluation, so that `refused` stays a compile-time false in the
          * cold-start kernels, was measured: 1 % slower.) */
-        bool refused = !alive;
+        bool refused = !alive || idle_lane;
         long long b = b_in;
         SolverT sv(P, sm, ws, wy);
         if (GM == 2) {
@@ -190,7 +207,7 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
 #pragma unroll
                 for (int tt = 0; tt < TPL; ++tt)
                     tilted |= (sv.x[tt * 9 + 6] != 0.0 || sv.x[tt * 9 + 7] != 0.0) ? 1 : 0;
-                if (sv.grp.any(tilted != 0) && alive) { /* broken promise: no solve, say so */
+                if (sv.grp.any(tilted != 0) && alive && !idle_lane) { /* broken promise: no solve, say so */
                     if ((MINB < 3) && A.rows) {
                         double *row = A.rows + b * A.row_stride;
                         const int nx = (A.rows_kind == 1 ? 3 : 9) * N, nd = (A.rows_kind == 1 ? 3 : (A.rows_kind == 2 ? 9 : 19)) * N;
@@ -254,7 +271,7 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
                 if (!__syncthreads_or(go)) break;
                 if (go) sv.template iterate<false>();
             }
-            if (refused || !alive) return;
+            if (refused || !alive || idle_lane) return;
             sv.finish(st);
         } else {
             if (refused) return;
@@ -390,15 +407,15 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
         (void)N;
     };
     if constexpr (SCHED == 1) {
-        constexpr int PPW = 32 / LANES;
+        constexpr int PPW = GMap::GPW;
         const long long ntasks = (A.B + PPW - 1) / PPW;
         for (;;) {
             long long ti = 0;
             if ((threadIdx.x & 31) == 0) ti = (long long)atomicAdd(A.queue, 1ull);
             ti = __shfl_sync(0xffffffffu, ti, 0);
             if (ti >= ntasks) break;
-            const long long b = ti * PPW + (threadIdx.x & 31) / LANES;
-            if (b < A.B) solve_one(b, true, 0);
+            const long long b = ti * PPW + gib % PPW;
+            if (b < A.B && !idle_lane) solve_one(b, true, 0);
             __syncwarp();
         }
     } else if constexpr (SCHED == 2) {
@@ -491,7 +508,7 @@ se3mpc_solve_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_c
             const long long b = blk * GPB + gib;
             if constexpr (LOCK)
                 solve_one(b < A.B ? b : A.B - 1, b < A.B, 0);
-            else if (b < A.B)
+            else if (b < A.B && !idle_lane)
                 solve_one(b, true, 0);
         }
     }
@@ -524,14 +541,15 @@ template <int LANES, int TPL, int BLOCK, bool TILT>
 __global__ void __launch_bounds__(BLOCK)
 se3mpc_extract_kernel(const __grid_constant__ dart_se3mpc_params P, const __grid_constant__ ExtractArgs A)
 {
-    constexpr int GPB = BLOCK / LANES;
-    const int gib = threadIdx.x / LANES;
+    using GMap = GroupMap<LANES, BLOCK>;
+    constexpr int GPB = GMap::GPB;
+    const int gib = GMap::gib();
     const long long rounds = (A.B + GPB - 1) / GPB;
     for (long long blk = blockIdx.x; blk < rounds; blk += gridDim.x) {
         __syncwarp();
         const long long b = blk * GPB + gib;
-        if (b < A.B) {
-            Solver<SubWarp<LANES>, TPL, 0, false, TILT> sv(P, nullptr, nullptr, nullptr);
+        if (b < A.B && !GMap::idle()) {
+            Solver<typename GroupOf<LANES>::type, TPL, 0, false, TILT> sv(P, nullptr, nullptr, nullptr);
 #pragma unroll
             for (int tt = 0; tt < TPL; ++tt) {
                 const int k = sv.grp.lane() * TPL + tt;
@@ -566,6 +584,7 @@ struct KernelSet {
     const void *fn[3][2];
     const void *extract_fn[2]; /* [tilt] */
     int lanes, tpl, block, minb;
+    int gpb;      /* problems per block */
     int resident; /* blocks per SM the shared-memory carve-out is sized for (default: minb) */
 };
 
@@ -585,6 +604,7 @@ KernelSet make_kernel_set()
     k.tpl = TPL;
     k.block = BLK;
     k.minb = MINB;
+    k.gpb = GroupMap<LANES, BLK>::GPB;
     k.resident = MINB;
     return k;
 }
@@ -599,5 +619,7 @@ KernelSet kernel_set_l8_occ3();
 KernelSet kernel_set_l8_b64();
 KernelSet kernel_set_l16_occ3();
 KernelSet kernel_set_l32_occ3();
+KernelSet kernel_set_l6();
+KernelSet kernel_set_l6_occ5();
 
 } /* namespace dartb200 */

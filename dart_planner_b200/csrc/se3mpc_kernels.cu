@@ -67,6 +67,14 @@ KernelChoice g_kernels[] = {
     make_choice(kernel_set_l8_occ3()), make_choice(kernel_set_l8_b64()),
     /* [7], [8] throughput builds for 8 < N <= 16 and 16 < N <= 32 */
     make_choice(kernel_set_l16_occ3()), make_choice(kernel_set_l32_occ3()),
+    /* [9], [10] horizons 5 and 6 (the reference's class default) on 6-lane groups, five problems
+     * per warp instead of four: latency build (2 blocks of 20 problems per SM) and throughput
+     * build (5 blocks of 10 problems per SM).  Same results as the 8-lane builds, but measured
+     * SLOWER (65 536 problems at N = 6: 275 / 268 us against 232 us in the 8-lane throughput
+     * build; 1 Mi: 4.07 against 3.32 ms): the shared block caps an SM at 50 problems on 10 warps
+     * against 48 on 12, five sub-warps wait for the slowest of five, and the kernel is bound by
+     * latency, not by the lanes it leaves idle.  Reachable with DART_SE3MPC_VARIANT=9 / 10 only. */
+    make_choice(kernel_set_l6()), make_choice(kernel_set_l6_occ5()),
 };
 std::mutex g_mu;
 int g_sms = 0;
@@ -93,12 +101,12 @@ unsigned g_prio_next[64] = {0};
 size_t stash_bytes_for(const KernelChoice &k, long long grid)
 {
     /* upper bound of Solver::ctx_doubles(1) over the gradient modes (se3mpc_core.cuh) */
-    const size_t S = 9 * (size_t)k.tpl, gpb = (size_t)(k.block / k.lanes);
+    const size_t S = 9 * (size_t)k.tpl, gpb = (size_t)k.set.gpb;
     const size_t ctx = 16 + 2 * ((S + 31) / 32) + 7 + (size_t)k.lanes * (4 * S + 3 * k.tpl);
     return (size_t)grid * (2 * gpb - 1) * ctx * sizeof(double);
 }
 
-int smem_bytes(const KernelChoice &k) { return (k.block / k.lanes) * SM_DOUBLES * (int)sizeof(double); }
+int smem_bytes(const KernelChoice &k) { return k.set.gpb * SM_DOUBLES * (int)sizeof(double); }
 
 int set_err(cudaError_t e, const char *what)
 {
@@ -188,7 +196,7 @@ int check_params(const dart_se3mpc_params *p)
 
 long long grid_for(const KernelChoice &k, long long B)
 {
-    const long long gpb = k.block / k.lanes;
+    const long long gpb = k.set.gpb;
     long long need = (B + gpb - 1) / gpb;
     long long cap = (long long)g_sms * k.occ_blocks;
     return need < cap ? need : cap;
@@ -456,7 +464,7 @@ int dart_se3mpc_extract_batch(const dart_se3mpc_params *params, int64_t B, int64
     a.B = B; a.ld = ld; a.T = thrust_vectors;
     a.acc = acc; a.att = att; a.rates = rates; a.thrust = thrust;
     void *args[] = {(void *)&P, (void *)&a};
-    const long long gpb = k->block / k->lanes;
+    const long long gpb = k->set.gpb;
     long long grid = (B + gpb - 1) / gpb;
     const long long cap = (long long)g_sms * 8;
     if (grid > cap) grid = cap;

@@ -416,6 +416,38 @@ def test_gpu_on_demand_breakpoints_and_step_bound(oracle_mod, monkeypatch, varia
     assert (np.abs(sol.x - ref.x).max(axis=1)[same] < 1e-8).all()
 
 
+@pytest.mark.parametrize("N", [5, 6])
+def test_gpu_six_lane_groups_agree_with_the_eight_lane_builds(oracle_mod, monkeypatch, N):
+    """Horizons 5 and 6 on 6-lane groups (five problems per warp, se3mpc_core.cuh SubWarp6;
+    DART_SE3MPC_VARIANT=9 latency build / 10 throughput build -- measured slower than the 8-lane
+    builds and therefore not the default): their reductions add in the order of the 8-lane butterfly
+    with two empty lanes, so the solves agree with the default builds to contraction noise with
+    identical counters, cold and warm, and with the oracle."""
+    import dart_planner_b200 as dp
+    p0, v0, goal = bench_inputs(61 + N, 4099, 1.5)          # ragged: the last warp holds 4 of 5 groups
+    cfg = dp.SE3MPCConfig(prediction_horizon=N, dt=0.1)
+    monkeypatch.delenv("DART_SE3MPC_VARIANT", raising=False)
+    base = dp.plan_batch(p0, v0, goal, cfg, to_host=True)
+    ref = oracle_mod.solve_batch(oracle_mod.make_params(horizon=N, dt=0.1), p0, v0, goal, nthreads=16)
+    _compare(base, ref)
+    xw = base.x.copy()
+    xw[:, 6 * N:] += np.random.default_rng(3).normal(0, 0.3, xw[:, 6 * N:].shape)
+    base_w = dp.plan_batch(p0, v0, goal, cfg, x_warm=xw, to_host=True)
+    for variant in ("9", "10"):
+        monkeypatch.setenv("DART_SE3MPC_VARIANT", variant)
+        got = dp.plan_batch(p0, v0, goal, cfg, to_host=True)
+        got_w = dp.plan_batch(p0, v0, goal, cfg, x_warm=xw, to_host=True)
+        monkeypatch.delenv("DART_SE3MPC_VARIANT")
+        for g, b in ((got, base), (got_w, base_w)):
+            np.testing.assert_allclose(g.x, b.x, rtol=0, atol=1e-10, err_msg=variant)
+            np.testing.assert_array_equal(g.nit, b.nit)
+            np.testing.assert_array_equal(g.nfev, b.nfev)
+            np.testing.assert_array_equal(g.status, b.status)
+            np.testing.assert_allclose(g.attitudes, b.attitudes, rtol=0, atol=1e-9)
+            np.testing.assert_allclose(g.body_rates, b.body_rates, rtol=0, atol=1e-7)
+        _compare(got, ref)
+
+
 def test_steps_in_flight_on_several_streams(oracle_mod):
     """A stream of planning steps with four in flight (one CUDA stream each) under
     `steps_in_flight`: the library picks the throughput build for the total load; every step's

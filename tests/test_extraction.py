@@ -107,6 +107,31 @@ def test_cuda_extraction_four_lanes_and_long_horizons(oracle_mod, monkeypatch):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("N", [5, 6])
+def test_cuda_extraction_six_lane_groups(oracle_mod, monkeypatch, N):
+    """6-lane groups (DART_SE3MPC_VARIANT=9, five problems per warp): invalid steps, the prev_R
+    carry across lanes (group-relative ballot / broadcast) and the degenerate-b1 fallback against
+    the oracle (pinned by the reference fixture), and the reference's G6 case at N = 6."""
+    import dart_planner_b200 as dp
+    monkeypatch.setenv("DART_SE3MPC_VARIANT", "9")
+    rng = np.random.default_rng(19 + N)
+    B = 103                                              # ragged: the last warp holds 3 of 5 groups
+    T = rng.normal(0, 4.0, (B, N, 3)) + np.array([0, 0, 12.0])
+    T[rng.random((B, N)) < 0.2] = 0.0
+    T[rng.random((B, N)) < 0.08] = np.array([3.0, 0, 0])
+    T[0, :3] = 0.0
+    T[1] = 0.0
+    op = oracle_mod.make_params(horizon=N, dt=0.05)
+    want = [oracle_mod.extract(op, np.concatenate([np.zeros(6 * N), T[b].ravel()])) for b in range(B)]
+    acc, att, rates, thr = (np.array([w[i] for w in want]) for i in range(4))
+    _check(dp.extract_batch(T, dp.SE3MPCConfig(prediction_horizon=N, dt=0.05)), att, rates, thr, acc, f"cuda 6 lanes N={N}")
+    if N == 6:
+        d, _ = _cases()
+        _check(dp.extract_batch(d["G6_T"][None], dp.SE3MPCConfig(prediction_horizon=6, dt=float(d["G6_dt"]))),
+               *_g6_expected(d), "cuda G6, 6 lanes")
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("N", [8, 6, 13, 40])
 def test_cuda_solve_epilogue_with_invalid_steps(N, oracle_mod):
     """The same branches through the public solve: min_thrust = 0 and a warm start whose shifted

@@ -104,30 +104,50 @@ class SharedHostBlock:
         self.nbytes = max(self.B, 1) * self.stride * 8
         self.owner = self.rank == dst
         name = [None]
+        err = None
+        self._shm = None
+        self._registered = False
+        self.rows = None
         if self.owner:
-            self._shm = shared_memory.SharedMemory(create=True, size=self.nbytes)
-            name[0] = self._shm.name
+            try:
+                self._shm = shared_memory.SharedMemory(create=True, size=self.nbytes)
+                name[0] = self._shm.name
+            except Exception as e:      # noqa: BLE001  (reported to every rank below)
+                err = e
         if self.world > 1:
             dist.broadcast_object_list(name, src=dst, group=group)
-        if not self.owner:
-            self._shm = shared_memory.SharedMemory(name=name[0])
-            try:        # the creating rank unlinks the segment; attaching ranks must not (Python < 3.13 tracks them too)
-                from multiprocessing import resource_tracker
-                resource_tracker.unregister(self._shm._name, "shared_memory")
-            except Exception:
-                pass
-        self.rows = np.ndarray((max(self.B, 1), self.stride), dtype=np.float64, buffer=self._shm.buf)
-        self.ptr = self.rows.ctypes.data
-        self._registered = False
-        if register:
-            import torch
-            rc = torch.cuda.cudart().cudaHostRegister(self.ptr, self.nbytes, 1 | 2)   # portable | mapped
-            if int(rc) != 0:
-                self.close()
-                raise RuntimeError(f"cudaHostRegister of the shared result block failed ({int(rc)})")
-            self._registered = True
+        if err is None and name[0] is None:
+            err = RuntimeError("the owning rank could not create the shared result block")
+        if err is None:
+            try:
+                if not self.owner:
+                    self._shm = shared_memory.SharedMemory(name=name[0])
+                    try:    # the creating rank unlinks the segment; attaching ranks must not (Python < 3.13 tracks them too)
+                        from multiprocessing import resource_tracker
+                        resource_tracker.unregister(self._shm._name, "shared_memory")
+                    except Exception:
+                        pass
+                self.rows = np.ndarray((max(self.B, 1), self.stride), dtype=np.float64, buffer=self._shm.buf)
+                self.ptr = self.rows.ctypes.data
+                if register:
+                    import torch
+                    rc = torch.cuda.cudart().cudaHostRegister(self.ptr, self.nbytes, 1 | 2)   # portable | mapped
+                    if int(rc) != 0:
+                        raise RuntimeError(f"cudaHostRegister of the shared result block failed ({int(rc)})")
+                    self._registered = True
+            except Exception as e:      # noqa: BLE001
+                err = e
+        # Everybody is attached before anybody may finish and unlink -- and a rank that failed must
+        # not leave the others waiting in a later collective: the ranks agree on the outcome here
+        # and fail (or go on) TOGETHER.
         if self.world > 1:
-            dist.barrier(group)      # everybody is attached before anybody may finish and unlink
+            oks = [None] * self.world
+            dist.all_gather_object(oks, err is None, group=group)
+            if err is None and not all(oks):
+                err = RuntimeError(f"shared result block: ranks {[r for r, o in enumerate(oks) if not o]} failed to map it")
+        if err is not None:
+            self.close()
+            raise err
 
     def close(self):
         if getattr(self, "_shm", None) is None:

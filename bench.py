@@ -418,7 +418,11 @@ def main():
                 ring[i % nsets].solve_device(streams[i % depth])
             barrier()
             n0 = L.dart_launch_count()
-            torch.cuda._sleep(2_000_000)     # ~1 ms of device-side wait: the K launches are queued behind it
+            # device-side wait the K launches are queued behind: long enough for the host to issue all
+            # of them (~10 us each from Python), so that the device-timed region never waits for
+            # the host -- one timed region of 200 steps is 3 ms, a hiccup of the issuing thread (GIL
+            # hand-over to the clock sampler, a page fault) would otherwise show up as a slower GPU
+            torch.cuda._sleep(int(min(max(2_000_000, args.steps * 30_000), 60_000_000)))
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             for st in streams[1:]:

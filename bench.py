@@ -33,7 +33,7 @@ UNIT = "solves/s"
 L2_FLUSH_BYTES = 256 << 20
 L2_BYTES = 126 << 20
 E2E_DEPTH = 3
-VALUE_DEPTH = 4
+VALUE_DEPTH = int(os.environ.get("DART_BENCH_DEPTH", "4"))
 
 
 def workload_inputs(B, seed):

@@ -233,13 +233,24 @@ def sharded_config_legs(torch, dist, dp, params, world, rank, stream, dt):
     v0 = rng.normal(0, 0.5, (Bg, 3))
     goal = np.tile([10.0, 0.0, 5.0], (Bg, 1))
     lo, hi = shard_range(Bg, world, rank)
+    # the replicated map: every rank holds the 256^3 grid of configs[2]; rank 0 rasterises the 64
+    # spheres and ONE broadcast copies its cells into the other ranks' replicas (outside the timed
+    # regions: the map is built once, the solves only read their local replica)
+    from dart_planner_b200.sharding import replicate_map
+    grid = dp.DenseOccupancyGrid((256, 256, 256), (-128, -128, -128), 0.2)
+    if rank == 0:
+        wr = np.random.default_rng(2)
+        grid.add_obstacles(wr.uniform(-20, 20, (64, 3)), wr.uniform(0.5, 2.0, 64))
+    torch.cuda.synchronize()
+    replicate_map(grid, src=0)
     for outputs, transport in (("solution", "host_block"), ("solution", "gather"), ("all", "gather")):
         how = "written into a shared host block" if transport == "host_block" else "gathered to rank 0 host memory"
-        key = f"configs[3] 1 Mi Monte-Carlo solves sharded by problem index, {outputs} rows {how}"
+        key = f"configs[3] 1 Mi Monte-Carlo solves sharded by problem index, replicated map, {outputs} rows {how}"
         try:
             # (the shared host block either maps on every rank or raises on every rank: the ranks
             # stay in step and the leg is skipped together, e.g. on a box with a small /dev/shm)
             solver = ShardedSolver(params, outputs=outputs, transport=transport)
+            solver.set_map(grid, 1.5, 0.6)      # fused is_trajectory_safe against the local replica
             solver.stage(p0[lo:hi], v0[lo:hi], goal[lo:hi], presliced=True, global_B=Bg)
             solver.run()                # maps the shared block
         except Exception as e:          # noqa: BLE001
@@ -270,10 +281,15 @@ def sharded_config_legs(torch, dist, dp, params, world, rank, stream, dt):
             # bit-identity: rank 0 alone solves a sample spread over every shard
             idx = np.arange(0, Bg, 257)
             alone = dp.plan_batch(p0[idx], v0[idx], goal[idx], dp.SE3MPCConfig(prediction_horizon=int(params.horizon), dt=dt),
-                                  to_host=True)
+                                  grid=grid, safety_margin=1.5, collision_threshold=0.6, to_host=True)
             leg["identical_to_one_gpu_on_sample"] = bool(
                 np.array_equal(sol.x[idx], alone.x) and np.array_equal(sol.cost[idx], alone.cost)
-                and np.array_equal(sol.nfev[idx], alone.nfev) and np.array_equal(sol.status[idx], alone.status))
+                and np.array_equal(sol.nfev[idx], alone.nfev) and np.array_equal(sol.status[idx], alone.status)
+                and sol.first_hit is not None and np.array_equal(sol.first_hit[idx], alone.first_hit))
+            leg["map"] = "256^3 grid, 64 spheres, replicated per GPU by one broadcast from rank 0; fused is_trajectory_safe"
+            leg["unsafe_fraction"] = float((sol.first_hit >= 0).mean()) if sol.first_hit is not None else None
+            if sol.first_hit is not None:      # first colliding step per trajectory (-1: safe)
+                leg["first_hit_hist"] = {int(k): int(v) for k, v in zip(*np.unique(sol.first_hit, return_counts=True))}
             leg["sample"] = int(len(idx))
             leg["nit_hist"] = np.bincount(sol.nit, minlength=4).tolist()
         out[key] = leg

@@ -13,9 +13,9 @@ from .mapper import DenseOccupancyGrid, SensorObservation  # noqa: F401
 from .mission import BatchedMissionGoals, SemanticWaypoint  # noqa: F401
 from .wire import SignedEnvelope  # noqa: F401
 from .closed_loop import ClosedLoopSim  # noqa: F401
-from .sharding import ShardedSolver, shard_range  # noqa: F401
+from .sharding import ShardedSolver, replicate_map, shard_range  # noqa: F401
 
 __all__ = ["SE3MPCConfig", "load_planner_config", "DroneState", "Trajectory", "SE3MPCPlanner",
            "BatchSolution", "plan_batch", "extract_batch", "solve_batch_tensors", "DenseOccupancyGrid", "SensorObservation", "ClosedLoopSim",
            "BatchedMissionGoals", "SemanticWaypoint", "SignedEnvelope",
-           "ShardedSolver", "shard_range"]
+           "ShardedSolver", "replicate_map", "shard_range"]

@@ -84,6 +84,28 @@ def gather_row_blocks(local, counts: List[int], dst: int = 0, group=None, recv=N
     return recv, width
 
 
+def replicate_map(grid, src: int = 0, group=None):
+    """The replicated map of BASELINE configs[3]: every rank holds a `DenseOccupancyGrid` of the same
+    geometry on its own GPU (each rank constructs its own), and the cells of rank `src` -- the map
+    the mapper built there -- are copied into all of them by ONE broadcast (256^3 float32 cells:
+    64 MiB over NVLink).  Read-only afterwards: every rank's solves query their local replica, no
+    map traffic crosses a link during a solve.  Returns `grid`; a no-op for a single process."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return grid
+    mine = (grid.nx, grid.ny, grid.nz, tuple(grid.origin_voxel), grid.resolution, grid.prob_prior, grid.dtype)
+    geo = [mine if dist.get_rank(group) == src else None]
+    dist.broadcast_object_list(geo, src=src, group=group)
+    same = [None] * dist.get_world_size(group)
+    dist.all_gather_object(same, tuple(geo[0]) == mine, group=group)      # fail together, not in the broadcast
+    if not all(same):
+        raise ValueError(f"replicate_map: ranks {[r for r, o in enumerate(same) if not o]} hold a grid of another "
+                         f"geometry than rank {src}'s {geo[0]}")
+    dist.broadcast(grid.occ, src=src, group=group)
+    return grid
+
+
 class SharedHostBlock:
     """One (B, stride) float64 block in POSIX shared memory, mapped by every rank of the group
     (one process per GPU on one box) and page-locked for each rank's GPU: rank r's kernel writes the
@@ -188,7 +210,11 @@ class ShardedSolver:
     (`SharedHostBlock`) and every rank's kernel writes its slice of result rows straight into it
     over its own PCIe link (zero-copy, full 128-byte lines); a barrier ends the call and `dst` reads
     host memory.  No result crosses NVLink and nothing funnels through `dst`'s link: 1 Mi problems
-    reach rank 0's host memory 3-5x sooner (bench.py, `sharded_configs`).  Needs N <= 25 (rows)."""
+    reach rank 0's host memory 3-5x sooner (bench.py, `sharded_configs`).  Needs N <= 25 (rows).
+
+    ``set_map(grid, safety_margin, collision_threshold)`` attaches this rank's replica of the map
+    (`replicate_map`): every solve then runs the fused `is_trajectory_safe` check on its solved
+    positions against the LOCAL replica and the rows carry its result (`HostSolution.first_hit`)."""
 
     def __init__(self, params, *, dst: int = 0, group=None,
                  solve_fn: Optional[Callable] = None, outputs: str = "all",
@@ -206,7 +232,16 @@ class ShardedSolver:
         self._ws = None
         self._recv = None
         self._pinned = None
+        self._map = None
         self.last_timing = {}
+
+    def set_map(self, grid, safety_margin: float = 1.0, collision_threshold: float = 0.6):
+        """This rank's replica of the occupancy grid (None detaches it): the solves of the CUDA row
+        path also run the fused trajectory safety check against it (explicit_geometric_mapper.py:
+        195-219); the result travels in the rows ("all" and "solution" rows; controls rows carry none)."""
+        self._map = None if grid is None else (grid, float(safety_margin), float(collision_threshold))
+        if self._ws is not None:
+            self._ws.set_map(*(self._map or (None,)))
 
     # -- local solves -----------------------------------------------------------------------
     def _solve_local(self, p0, v0, goal):
@@ -218,6 +253,8 @@ class ShardedSolver:
 
         if self._ws is None or self._ws.B != max(b, 1):
             self._ws = BatchWorkspace(self.params, max(b, 1), pinned=False, outputs=self.outputs)
+            if self._map is not None:
+                self._ws.set_map(*self._map)
         return self._ws
 
     def _rows_local(self, p0, v0, goal):

@@ -113,3 +113,40 @@ def test_grid_penalty_mode_matches_self_oracle(oracle_mod):
     # penalty mode without a grid is rejected
     with pytest.raises(ValueError):
         dp.plan_batch(p0[:4], v0[:4], goal[:4], cfg, obstacle_penalty=True)
+
+
+@pytest.mark.parametrize("transport", ["gather", "host_block"])
+@pytest.mark.parametrize("outputs", ["solution", "all"])
+def test_sharded_solver_with_the_replicated_map(outputs, transport):
+    """BASELINE configs[3] (Monte-Carlo initial states, one goal, sharded by problem index, map
+    replicated per GPU): `ShardedSolver.set_map` runs the fused safety check against the rank's
+    replica and the result rows carry it -- one process here (the multi-rank plumbing of the map
+    is the gloo test of `replicate_map`); identical to the single-GPU fused check."""
+    import dart_planner_b200 as dp
+    from dart_planner_b200.config import make_params
+    centers, radii = config3_world()
+    grid = dp.replicate_map(dp.DenseOccupancyGrid((256, 256, 256), (-128, -128, -128), 0.2))
+    grid.add_obstacles(centers, radii)
+    B = 20011
+    rng = np.random.default_rng(3)
+    p0 = rng.normal((0, 0, 2), 1.0, (B, 3))
+    v0 = rng.normal(0, 0.5, (B, 3))
+    goal = np.tile([10.0, 0.0, 5.0], (B, 1))
+    cfg = dp.SE3MPCConfig(prediction_horizon=8, dt=0.1)
+    solver = dp.ShardedSolver(make_params(cfg), outputs=outputs, transport=transport)
+    solver.set_map(grid, 1.5, 0.6)
+    sol = solver.solve(p0, v0, goal, copy=True)
+    one = dp.plan_batch(p0, v0, goal, cfg, grid=grid, safety_margin=1.5, collision_threshold=0.6)
+    want = one.first_hit.cpu().numpy()
+    assert sol.first_hit is not None
+    np.testing.assert_array_equal(sol.first_hit, want)
+    assert len(np.unique(want)) >= 4           # (this goal sits next to a sphere: the first colliding step varies)
+    host = one.numpy()
+    np.testing.assert_array_equal(sol.nfev, host.nfev)
+    np.testing.assert_allclose(sol.x, host.x, rtol=0, atol=1e-11)     # rows: latency build; plan_batch: throughput build
+    solver.set_map(None)
+    again = solver.solve(p0, v0, goal, copy=True)
+    assert again.first_hit is None
+    np.testing.assert_array_equal(again.x, sol.x)
+    if transport == "host_block":
+        solver._block.close()

@@ -208,3 +208,54 @@ def test_sharded_row_gather_all_row_kinds(oracle_mod, world, B):
         np.testing.assert_allclose(rates, ref.body_rates, rtol=0, atol=1e-9)
     tv, cost, nfev = got["controls"]
     assert np.array_equal(tv.reshape(B, -1), ref.x[:, 48:]) and np.array_equal(cost, ref.cost) and np.array_equal(nfev, ref.nfev)
+
+
+def _map_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from types import SimpleNamespace
+        from dart_planner_b200.sharding import replicate_map
+
+        def host_grid(shape):       # what replicate_map reads of a DenseOccupancyGrid (the real one lives on a GPU)
+            nx, ny, nz = shape
+            return SimpleNamespace(nx=nx, ny=ny, nz=nz, origin_voxel=(-8, -6, -4), resolution=0.5, prob_prior=0.5,
+                                   dtype="float32", occ=torch.full((nz, ny, nx), 0.5, dtype=torch.float32))
+        grid = host_grid((16, 12, 8))                   # every rank constructs its own
+        if rank == 0:       # the map the mapper built on the source rank
+            grid.occ.copy_(torch.rand((8, 12, 16), generator=torch.Generator().manual_seed(5)).to(grid.occ.dtype))
+        assert replicate_map(grid, src=0) is grid
+        want = torch.rand((8, 12, 16), generator=torch.Generator().manual_seed(5)).to(grid.occ.dtype)
+        ok = bool(torch.equal(grid.occ, want))
+        # another geometry on one rank: every rank raises (nobody is left inside the broadcast)
+        other = host_grid((16, 12, 8 if rank == 0 else 9))
+        try:
+            replicate_map(other, src=0)
+            raised = False
+        except ValueError:
+            raised = True
+        dist.barrier()
+        q.put((rank, ok, raised))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_replicate_map_broadcasts_the_source_ranks_cells():
+    """BASELINE configs[3]'s replicated map: one broadcast of the source rank's cells into every
+    rank's own grid; a geometry mismatch fails on every rank together."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    world = 2
+    procs = [ctx.Process(target=_map_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert got == [(0, True, True), (1, True, True)]

@@ -291,9 +291,14 @@ static int launch_solve(const dart_se3mpc_params *params, const SolveArgs &a, vo
          * is about cold starts; a warm-started population near its goals is not a set of stragglers).
          * Near-goal radius: where the position term of the start's objective, ~ w_pos N r^2 / 3,
          * falls below the scale of the thrust term the reference's gradient mis-states,
-         * ~ w_thrust (m g)^2 N / 3 -- a scheduling heuristic, results do not depend on it. */
+         * ~ w_thrust (m g)^2 N / 3 -- a scheduling heuristic, results do not depend on it.
+         * Not with the fused plant step of the closed loop: that launch overwrites the state in
+         * place, and a member of the list met again in a regular round is recognised by the
+         * predicate on the state it loads -- after its priority-round solve has moved it, the drone
+         * could leave the radius and be stepped twice (tests/test_gpu_closed_loop.py,
+         * test_run_in_sub_populations_changes_no_result). */
         if (k->minb >= 3 && DART_THROUGHPUT_SCHED == 2 && a.B >= PRIO_MIN_B && a.B < (1ll << 31) &&
-            a.x_warm == nullptr && params->w_pos > 0.0 && !getenv("DART_SE3MPC_NO_PRIO")) {
+            a.x_warm == nullptr && a.p_next == nullptr && params->w_pos > 0.0 && !getenv("DART_SE3MPC_NO_PRIO")) {
             StashBuf &pb = g_prio[dev][g_prio_next[dev]++ % PRIO_RING];
             const size_t need = 16 + (size_t)PRIO_CAP * sizeof(int); /* fixed: allocated once per slot */
             if (pb.done) {

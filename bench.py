@@ -323,7 +323,8 @@ def sharded_config_legs(torch, dist, dp, params, world, rank, stream, dt):
 
     closed_loop()
     cl_ms, pos = closed_loop()
-    leg = {"value": Bd * 100 / (cl_ms * 1e-3), "unit": UNIT, "total_ms": cl_ms, "launches_per_gpu": 100,
+    leg = {"value": Bd * 100 / (cl_ms * 1e-3), "unit": UNIT, "total_ms": cl_ms, "launches_per_gpu": 100 * sim.default_parts(),
+           "sub_populations_in_flight": sim.default_parts(),
            "n_gpus": world, "scaling": "strong", "drones_per_gpu": int(hi - lo)}
     if rank == 0 and world > 1:
         # the first shard's final positions must equal a single-GPU run of the same drones
@@ -855,7 +856,8 @@ def main():
         torch.cuda.synchronize()
         cl_ms = ea.elapsed_time(eb)
         others["configs[4] closed loop: 65536 drones x 100 replans (10 s at 10 Hz), warm starts, resident state"] = {
-            "value": Bs * 100 / (cl_ms * 1e-3), "unit": UNIT, "total_ms": cl_ms, "launches": 100}
+            "value": Bs * 100 / (cl_ms * 1e-3), "unit": UNIT, "total_ms": cl_ms,
+            "launches": 100 * sim.default_parts(), "sub_populations_in_flight": sim.default_parts()}
         # mapper: one LiDAR-like scan (update_map) and the batched queries, the HBM/L2-bound side
         rngm = np.random.default_rng(3)
         R = 200_000

@@ -91,8 +91,11 @@ class ClosedLoopSim:
         self.steps_done += 1
 
     def default_parts(self) -> int:
-        """Sub-populations `run` keeps in flight: 4 096 drones or more each, at most four."""
-        return max(1, min(4, self.B // 4096))
+        """Sub-populations `run` keeps in flight (measured, tools/closed_loop_parts.py, 100 replans on
+        one B200, ms for 1 / 2 / 3 / 4 parts): 65 536 drones 22.0 / 21.6 / 21.6 / 21.7; 32 768: 11.5 /
+        10.8 / 10.8 / 11.1; 16 384: 6.8 / 5.6 / 5.5 / 5.6; 8 192 (one GPU's share of 65 536 on eight):
+        4.6 / 3.5 / 3.3 / 3.6 -- the fewer waves of blocks a step has, the more its idle tail costs."""
+        return 2 if self.B >= 49152 else (3 if self.B >= 6144 else 1)
 
     def run(self, steps: int, stream=None, track_counters: bool = True, record: bool = False,
             parts: Optional[int] = None):
